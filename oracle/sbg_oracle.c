@@ -360,6 +360,7 @@ int orc_search_7lut(const uint64_t *tables, int n, const uint64_t *target, const
       const int stale_o = cache_lookup(&outer_cache, g[0], g[1], g[2]);
       const int stale_m = cache_lookup(&middle_cache, g[3], g[4], g[5]);
       if (stats && (stale_o || stale_m)) stats->stale_cache_rows++;
+      const int row_is_stale = stale_o || stale_m;
       for (int f = 0; f < 256; f++) { /* lut.c:70-74, from the triple actually cached */
         orc_lut_ttable((uint8_t)f, tables + 4 * outer_cache.gates[0],
             tables + 4 * outer_cache.gates[1], tables + 4 * outer_cache.gates[2], t_outer[f]);
@@ -382,6 +383,7 @@ int orc_search_7lut(const uint64_t *tables, int n, const uint64_t *target, const
           ret[1] = func_middle;
           ret[2] = fi;
           for (int m = 0; m < 7; m++) ret[3 + m] = g[m];
+          if (stats) stats->stale_hit = (uint64_t)row_is_stale;
           found = 1;
           break;
         }
@@ -392,4 +394,82 @@ int orc_search_7lut(const uint64_t *tables, int n, const uint64_t *target, const
   free(t_middle);
   free(list);
   return found;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* "Minimum key over a share" forms (see sbg_oracle.h).  Same loops as above, restricted to a share
+   and reporting where the first match sits instead of building ret[]. */
+
+uint64_t orc_search5_key(const uint64_t *tables, int n, const uint64_t *target, const uint64_t *mask,
+    const int8_t *inbits, const uint8_t *func_order, int part, int nparts) {
+  int rows[10][5];
+  for (int k = 0; k < 10; k++) orc_order5_row(k, rows[k]);
+  const int64_t total = orc_n_choose_k(n, 5);
+  uint16_t nums[5] = {0, 1, 2, 3, 4};
+  for (int64_t r = 0; r < total; r++, orc_next_combination(nums, 5, n)) {
+    if (r % nparts != part) continue;
+    if (rejected_by_inbits(nums, 5, inbits)) continue;
+    uint64_t tt[5 * 4];
+    for (int m = 0; m < 5; m++) memcpy(tt + 4 * m, tables + 4 * nums[m], 32);
+    if (!orc_check_n_lut_possible(5, target, mask, tt)) continue;
+    for (int k = 0; k < 10; k++) {
+      const int *o = rows[k];
+      for (int pos = 0; pos < 256; pos++) {
+        uint64_t t_outer[4];
+        uint8_t fi, seen;
+        orc_lut_ttable(func_order[pos], tt + 4 * o[0], tt + 4 * o[1], tt + 4 * o[2], t_outer);
+        if (orc_solve_inner(t_outer, tt + 4 * o[3], tt + 4 * o[4], target, mask, &fi, &seen)) {
+          return (uint64_t)r << 12 | (uint64_t)k << 8 | (uint64_t)pos;
+        }
+      }
+    }
+  }
+  return UINT64_MAX;
+}
+
+uint64_t orc_decomp7_key(const uint64_t *tables, const uint64_t *target, const uint64_t *mask,
+    const uint16_t *list, int count, const uint8_t *outer_order, const uint8_t *middle_order,
+    int part, int nparts) {
+  int rows[70][7];
+  for (int k = 0; k < 70; k++) orc_order7_row(k, rows[k]);
+  uint64_t (*t_outer)[4] = malloc(256 * 32);
+  uint64_t (*t_middle)[4] = malloc(256 * 32);
+  if (t_outer == NULL || t_middle == NULL) abort();
+  uint64_t key = UINT64_MAX;
+  for (int i = part; i < count && key == UINT64_MAX; i += nparts) {
+    const uint16_t *tuple = list + 7 * i;
+    /* State of the reference's outer cache on entry to tuple i: left by row 69 of tuple i-1
+       (lut.c:432-435), wherever that tuple was processed. */
+    lut_cache outer_cache = {0, {0, 0, 0}}, middle_cache = {0, {0, 0, 0}};
+    if (i > 0) {
+      const uint16_t *prev = list + 7 * (i - 1);
+      cache_lookup(&outer_cache, prev[rows[69][0]], prev[rows[69][1]], prev[rows[69][2]]);
+      cache_lookup(&middle_cache, prev[rows[69][3]], prev[rows[69][4]], prev[rows[69][5]]);
+    }
+    for (int k = 0; k < 70 && key == UINT64_MAX; k++) {
+      uint16_t g[7];
+      for (int m = 0; m < 7; m++) g[m] = tuple[rows[k][m]];
+      cache_lookup(&outer_cache, g[0], g[1], g[2]);
+      cache_lookup(&middle_cache, g[3], g[4], g[5]);
+      for (int f = 0; f < 256; f++) {
+        orc_lut_ttable((uint8_t)f, tables + 4 * outer_cache.gates[0],
+            tables + 4 * outer_cache.gates[1], tables + 4 * outer_cache.gates[2], t_outer[f]);
+        orc_lut_ttable((uint8_t)f, tables + 4 * middle_cache.gates[0],
+            tables + 4 * middle_cache.gates[1], tables + 4 * middle_cache.gates[2], t_middle[f]);
+      }
+      for (int po = 0; po < 256 && key == UINT64_MAX; po++) {
+        for (int pm = 0; pm < 256; pm++) {
+          uint8_t fi, seen;
+          if (orc_solve_inner(t_outer[outer_order[po]], t_middle[middle_order[pm]],
+              tables + 4 * g[6], target, mask, &fi, &seen)) {
+            key = (uint64_t)i << 23 | (uint64_t)k << 16 | (uint64_t)po << 8 | (uint64_t)pm;
+            break;
+          }
+        }
+      }
+    }
+  }
+  free(t_outer);
+  free(t_middle);
+  return key;
 }

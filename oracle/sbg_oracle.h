@@ -32,6 +32,7 @@ typedef struct {
   uint64_t tuples_feasible;  /* feasible combinations (5-LUT: tried; 7-LUT: length of the list) */
   uint64_t candidates;       /* C-units: (tuple, ordering, fo[, fm]) candidates decided */
   uint64_t stale_cache_rows; /* 7-LUT rows evaluated with the reference's stale outer cache */
+  uint64_t stale_hit;        /* 1 if the returned match came from such a row */
 } orc_stats;
 
 uint64_t orc_rng_next(orc_rng *rng);
@@ -58,6 +59,17 @@ int orc_search_7lut(const uint64_t *tables, int n, const uint64_t *target, const
    (7 x uint16 each) in lexicographic order, returns how many. */
 int orc_filter_7lut(const uint64_t *tables, int n, const uint64_t *target, const uint64_t *mask,
     const int8_t *inbits, uint16_t *list, int cap, orc_stats *stats);
+
+/* The same searches expressed as "minimum key over a share of the work", which is how the sharded
+   implementations (GPU parts, ranks) are specified.  part/nparts select the combinations (5-LUT)
+   or list entries (7-LUT) whose rank / index is congruent to part modulo nparts; the orders are the
+   already shuffled function orders; no RNG is involved.  Keys: 5-LUT rank<<12 | k<<8 | pos;
+   7-LUT idx<<23 | k<<16 | pos_outer<<8 | pos_middle; UINT64_MAX if the share holds no match. */
+uint64_t orc_search5_key(const uint64_t *tables, int n, const uint64_t *target, const uint64_t *mask,
+    const int8_t *inbits, const uint8_t *func_order, int part, int nparts);
+uint64_t orc_decomp7_key(const uint64_t *tables, const uint64_t *target, const uint64_t *mask,
+    const uint16_t *list, int count, const uint8_t *outer_order, const uint8_t *middle_order,
+    int part, int nparts);
 
 /* Row k (0..69) of the ordering table at lut.c:396-415, regenerated from its rule. */
 void orc_order7_row(int k, int *row7);

@@ -1,0 +1,837 @@
+// sbg_api.cu -- host side of libsboxgates_b200.so: the C ABI declared in
+// include/sboxgates_b200.h.  No search logic runs on the CPU here except the O(256) decode of the
+// winning key into the reference's ret[] vocabulary (sbg_finish5 / sbg_finish7); there is no CPU
+// fallback -- without a CUDA device sbg_create() fails.
+#include "sbg_device.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/sboxgates_b200.h"
+
+using namespace sbg;
+
+namespace {
+
+// ---- combinatorics and ordering tables (host copies) -------------------------------------------
+
+uint64_t h_binom[501][8];
+int h_rows7[70][7];
+int h_rows5[10][5];
+bool g_tables_ready = false;
+
+void build_host_tables() {
+  if (g_tables_ready) return;
+  for (int m = 0; m <= 500; m++) {
+    for (int r = 0; r < 8; r++) {
+      if (r > m) {
+        h_binom[m][r] = 0;
+      } else if (r == 0) {
+        h_binom[m][r] = 1;
+      } else {
+        h_binom[m][r] = h_binom[m - 1][r - 1] + (r <= m - 1 ? h_binom[m - 1][r] : 0);
+      }
+    }
+  }
+  // lut.c:189,224-229: outer = 3-subsets of {0..4} in lexicographic order, rest ascending.
+  int k = 0;
+  for (int a = 0; a < 5; a++) for (int b = a + 1; b < 5; b++) for (int c = b + 1; c < 5; c++) {
+    int w = 3;
+    h_rows5[k][0] = a; h_rows5[k][1] = b; h_rows5[k][2] = c;
+    for (int i = 0; i < 5; i++) {
+      if (i != a && i != b && i != c) h_rows5[k][w++] = i;
+    }
+    k++;
+  }
+  // lut.c:396-415: outer = 3-subsets of {0..6} (lexicographic), middle = 3-subsets of the other
+  // four (lexicographic), kept iff min(outer) < min(middle); last = the leftover position.
+  k = 0;
+  for (int a = 0; a < 7; a++) for (int b = a + 1; b < 7; b++) for (int c = b + 1; c < 7; c++) {
+    int rest[4], r = 0;
+    for (int i = 0; i < 7; i++) {
+      if (i != a && i != b && i != c) rest[r++] = i;
+    }
+    for (int skip = 3; skip >= 0; skip--) {
+      int mid[3], m = 0;
+      for (int i = 0; i < 4; i++) {
+        if (i != skip) mid[m++] = rest[i];
+      }
+      if (a >= mid[0]) continue;
+      h_rows7[k][0] = a; h_rows7[k][1] = b; h_rows7[k][2] = c;
+      h_rows7[k][3] = mid[0]; h_rows7[k][4] = mid[1]; h_rows7[k][5] = mid[2];
+      h_rows7[k][6] = rest[skip];
+      k++;
+    }
+  }
+  g_tables_ready = true;
+}
+
+void unrank_combination(uint64_t rank, int n, int t, uint16_t *out) {
+  int x = 0;
+  for (int pos = 0; pos < t; pos++) {
+    for (;; x++) {
+      const uint64_t cnt = h_binom[n - x - 1][t - pos - 1];
+      if (rank < cnt) break;
+      rank -= cnt;
+    }
+    out[pos] = (uint16_t)x++;
+  }
+}
+
+int popcount256(const uint64_t *m) {
+  return __builtin_popcountll(m[0]) + __builtin_popcountll(m[1]) + __builtin_popcountll(m[2])
+      + __builtin_popcountll(m[3]);
+}
+
+// Gathers the bits of `t` at the set positions of `mask` into the low bits of out[0..7].
+void compress_table(const uint64_t *t, const uint64_t *mask, uint32_t *out) {
+  uint64_t acc[4] = {0, 0, 0, 0};
+  int fill = 0;
+  for (int v = 0; v < 4; v++) {
+    uint64_t m = mask[v];
+    const uint64_t x = t[v];
+#if defined(__BMI2__)
+    const uint64_t bits = __builtin_ia32_pext_di(x, m);
+    const int cnt = __builtin_popcountll(m);
+#else
+    uint64_t bits = 0;
+    int cnt = 0;
+    while (m != 0) {
+      const int b = __builtin_ctzll(m);
+      m &= m - 1;
+      bits |= ((x >> b) & 1ull) << cnt;
+      cnt++;
+    }
+#endif
+    if (cnt == 0) continue;
+    acc[fill >> 6] |= bits << (fill & 63);
+    if ((fill & 63) + cnt > 64) acc[(fill >> 6) + 1] |= bits >> (64 - (fill & 63));
+    fill += cnt;
+  }
+  for (int v = 0; v < 4; v++) {
+    out[2 * v] = (uint32_t)acc[v];
+    out[2 * v + 1] = (uint32_t)(acc[v] >> 32);
+  }
+}
+
+}  // namespace
+
+// ---- handle ----------------------------------------------------------------------------------
+
+struct sbg_handle {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+
+  DevProblem *d_prob = nullptr;  // the problem in use (points into d_slots)
+  DevProblem *d_slots = nullptr; // kSlots device-resident problems
+  DevProblem *h_prob = nullptr;  // pinned staging copy
+  DevCtl *d_ctl = nullptr;
+  DevCtl *h_ctl = nullptr;       // pinned
+  DevParams7 *d_par7 = nullptr;
+  DevParams7 *h_par7 = nullptr;  // pinned
+  uint8_t *d_pos5 = nullptr;
+  uint8_t *h_pos5 = nullptr;     // pinned
+
+  uint64_t *d_hits = nullptr;    // unordered feasible tuples of this device
+  uint64_t *d_sorted = nullptr;  // sorted copy
+  uint64_t *d_list = nullptr;    // installed list (points into d_sorted or d_hits)
+  size_t hits_cap = 0;
+  void *d_cub = nullptr;
+  size_t cub_bytes = 0;
+  uint64_t *h_list = nullptr;    // pinned, SBG_LIST_CAP entries
+  uint32_t list_count = 0;
+  bool list_ready = false;
+
+  // host copies of the staged problems (for sbg_finish*); the one in use is mirrored below
+  struct HostProblem {
+    uint64_t tables[SBG_MAX_GATES][4];
+    uint64_t target[4];
+    uint64_t mask[4];
+    int n = 0;
+    int nw = 0;
+    bool ready = false;
+  };
+  HostProblem *slots = nullptr;  // kSlots entries
+  uint64_t (*tables)[4] = nullptr;
+  uint64_t *target = nullptr;
+  uint64_t *mask = nullptr;
+  int n = 0;
+  int nw = 0;
+  bool problem_ready = false;
+
+  uint64_t swept = 0;
+  uint64_t feasible = 0;
+  uint64_t launches = 0;      // our kernels
+  uint64_t lib_launches = 0;  // CUB radix-sort kernels
+  float ms[4] = {0, 0, 0, 0};
+  cudaEvent_t ev[8];
+  char err[512] = {0};
+};
+
+namespace {
+
+constexpr int kSlots = SBG_PROBLEM_SLOTS;
+
+int fail(sbg_handle *h, int code, const char *fmt, ...) {
+  if (h != nullptr) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(h->err, sizeof(h->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+#define SBG_CUDA(h, call)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      return fail((h), SBG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+          __FILE__, __LINE__);                                                             \
+    }                                                                                      \
+  } while (0)
+
+template <int NW, int P>
+size_t sweep_smem(int n) {
+  const int npad = (n + 3) & ~3;
+  return sizeof(uint32_t) * (size_t)(NW * npad + kWarpsPerCta * (1 << P) * 2 * NW);
+}
+
+template <int NW>
+size_t decomp_smem(int n) {
+  const int npad = (n + 3) & ~3;
+  return sizeof(uint32_t) * (size_t)(NW * npad);
+}
+
+// Persistent grid: as many CTAs as are resident at once, but no more than there is work for.
+template <typename Kernel>
+int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_warps) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+  if (per_sm < 1) per_sm = 1;
+  uint64_t want = (work_items_in_warps + kWarpsPerCta - 1) / kWarpsPerCta;
+  uint64_t cap = (uint64_t)per_sm * (uint64_t)h->sm_count;
+  if (want < 1) want = 1;
+  return (int)std::min(want, cap);
+}
+
+template <int P>
+int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
+  const int n = h->n;
+  const uint64_t tickets = (h_binom[n - 2][P] + nparts - 1) / nparts;
+  const unsigned long long cap = h->hits_cap;
+#define SBG_LAUNCH_SWEEP(NWV)                                                                  \
+  {                                                                                            \
+    const size_t smem = sweep_smem<NWV, P>(n);                                                 \
+    int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
+    if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
+    k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP);                       \
+  }
+  switch (h->nw) {
+    case 1: SBG_LAUNCH_SWEEP(1) break;
+    case 2: SBG_LAUNCH_SWEEP(2) break;
+    case 4: SBG_LAUNCH_SWEEP(4) break;
+    default: SBG_LAUNCH_SWEEP(8) break;
+  }
+#undef SBG_LAUNCH_SWEEP
+  h->launches++;
+  SBG_CUDA(h, cudaGetLastError());
+  return SBG_OK;
+}
+
+int launch_decomp7(sbg_handle *h, int part, int nparts) {
+  const int n = h->n;
+  const uint64_t items = (h->list_count + nparts - 1) / nparts;
+#define SBG_LAUNCH_DECOMP(NWV)                                                                 \
+  {                                                                                            \
+    const size_t smem = decomp_smem<NWV>(n);                                                   \
+    const int grid = grid_for(h, k_decomp7<NWV>, smem, items);                                 \
+    k_decomp7<NWV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_par7,        \
+        h->d_list, h->list_count, part, nparts);                                               \
+  }
+  switch (h->nw) {
+    case 1: SBG_LAUNCH_DECOMP(1) break;
+    case 2: SBG_LAUNCH_DECOMP(2) break;
+    case 4: SBG_LAUNCH_DECOMP(4) break;
+    default: SBG_LAUNCH_DECOMP(8) break;
+  }
+#undef SBG_LAUNCH_DECOMP
+  h->launches++;
+  SBG_CUDA(h, cudaGetLastError());
+  return SBG_OK;
+}
+
+int reset_ctl(sbg_handle *h) {
+  DevCtl *c = h->h_ctl;
+  memset(c, 0, sizeof(*c));
+  c->best = ~0ull;
+  c->stop_ticket = ~0ull;
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_ctl, c, sizeof(DevCtl), cudaMemcpyHostToDevice, h->stream));
+  return SBG_OK;
+}
+
+int fetch_ctl(sbg_handle *h) {
+  SBG_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost,
+      h->stream));
+  SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SBG_OK;
+}
+
+float elapsed(sbg_handle *h, int a, int b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) return 0.f;
+  return ms;
+}
+
+int sort_hits(sbg_handle *h, uint64_t *d_in, uint64_t *d_out, size_t count) {
+  size_t need = h->cub_bytes;
+  SBG_CUDA(h, cub::DeviceRadixSort::SortKeys(h->d_cub, need, d_in, d_out, (int)count, 0, 63,
+      h->stream));
+  h->lib_launches += 3;  // CUB's histogram + onesweep passes: library kernels, not ours
+  return SBG_OK;
+}
+
+// Phase 1 on this device: leaves the sorted local list (<= SBG_LIST_CAP) in d_sorted.
+int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
+  int rc;
+  int max_ctas = 0;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[0], h->stream);
+    if ((rc = launch_sweep<5>(h, part, nparts, max_ctas)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[1], h->stream);
+    if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+    h->ms[1] = elapsed(h, 0, 1);
+    if (!h->h_ctl->overflow) break;
+    if (attempt == 1) {
+      return fail(h, SBG_ERR_OVERFLOW, "7-LUT hit buffer (%zu entries) overflowed", h->hits_cap);
+    }
+    // Every prefix contributes at most SBG_LIST_CAP hits, and prefixes are handed out in order:
+    // with w warps in flight the buffer needs (w + 1) * SBG_LIST_CAP entries at most.
+    max_ctas = (int)std::max<size_t>(1, (h->hits_cap / SBG_LIST_CAP - 1) / kWarpsPerCta);
+  }
+  h->swept = h->h_ctl->swept;
+  const size_t total = (size_t)h->h_ctl->hit_count;
+  uint32_t keep = 0;
+  h->ms[2] = 0.f;
+  if (total > 0) {
+    cudaEventRecord(h->ev[2], h->stream);
+    if ((rc = sort_hits(h, h->d_hits, h->d_sorted, total)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[3], h->stream);
+    keep = (uint32_t)std::min<size_t>(total, SBG_LIST_CAP);
+  }
+  *count_out = keep;
+  return SBG_OK;
+}
+
+void build_params7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle_order) {
+  DevParams7 *p = h->h_par7;
+  memset(p, 0, sizeof(*p));
+  for (int pos = 0; pos < 256; pos++) p->pos_outer[outer_order[pos]] = (uint8_t)pos;
+  for (int pm = 0; pm < 256; pm++) {
+    const uint32_t f = middle_order[pm];
+    for (uint32_t s = 0; s < 16; s++) {
+      p->lo[s * 16 + (f & 15u & s)][pm >> 5] |= 1u << (pm & 31);
+      p->hi[s * 16 + ((f >> 4) & s)][pm >> 5] |= 1u << (pm & 31);
+    }
+  }
+}
+
+int run_decomp7(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
+    const uint8_t *middle_order, uint64_t *key) {
+  int rc;
+  *key = SBG_KEY_NONE;
+  h->ms[3] = 0.f;
+  if (h->list_count == 0) return SBG_OK;
+  build_params7(h, outer_order, middle_order);
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_par7, h->h_par7, sizeof(DevParams7), cudaMemcpyHostToDevice,
+      h->stream));
+  if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+  cudaEventRecord(h->ev[4], h->stream);
+  if ((rc = launch_decomp7(h, part, nparts)) != SBG_OK) return rc;
+  cudaEventRecord(h->ev[5], h->stream);
+  if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+  h->ms[3] = elapsed(h, 4, 5);
+  *key = h->h_ctl->best;
+  return SBG_OK;
+}
+
+int run_search5(sbg_handle *h, int part, int nparts, const uint8_t *func_order, uint64_t *key) {
+  int rc;
+  for (int pos = 0; pos < 256; pos++) h->h_pos5[func_order[pos]] = (uint8_t)pos;
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_pos5, h->h_pos5, 256, cudaMemcpyHostToDevice, h->stream));
+  if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+  cudaEventRecord(h->ev[6], h->stream);
+  if ((rc = launch_sweep<3>(h, part, nparts, 0)) != SBG_OK) return rc;
+  cudaEventRecord(h->ev[7], h->stream);
+  if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+  h->ms[0] = elapsed(h, 6, 7);
+  h->swept = h->h_ctl->swept;
+  h->feasible = h->h_ctl->feasible;
+  *key = h->h_ctl->best;
+  return SBG_OK;
+}
+
+bool valid_order(const uint8_t *order) {
+  if (order == nullptr) return false;
+  bool seen[256] = {false};
+  for (int i = 0; i < 256; i++) {
+    if (seen[order[i]]) return false;
+    seen[order[i]] = true;
+  }
+  return true;
+}
+
+}  // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------------
+
+extern "C" {
+
+int sbg_ordering_row(int width, int k, int *row) {
+  build_host_tables();
+  if (row == nullptr) return SBG_ERR_ARG;
+  if (width == 5 && k >= 0 && k < 10) {
+    for (int i = 0; i < 5; i++) row[i] = h_rows5[k][i];
+    return SBG_OK;
+  }
+  if (width == 7 && k >= 0 && k < 70) {
+    for (int i = 0; i < 7; i++) row[i] = h_rows7[k][i];
+    return SBG_OK;
+  }
+  return SBG_ERR_ARG;
+}
+
+void sbg_lut_table(uint8_t func, const uint64_t *in1, const uint64_t *in2, const uint64_t *in3,
+    uint64_t *out) {
+  for (int v = 0; v < 4; v++) {
+    uint64_t r = 0;
+    for (int m = 0; m < 8; m++) {
+      if ((func >> m) & 1) {
+        r |= ((m & 4) ? in1[v] : ~in1[v]) & ((m & 2) ? in2[v] : ~in2[v])
+            & ((m & 1) ? in3[v] : ~in3[v]);
+      }
+    }
+    out[v] = r;
+  }
+}
+
+int sbg_solve_inner(const uint64_t *in1, const uint64_t *in2, const uint64_t *in3,
+    const uint64_t *target, const uint64_t *mask, uint8_t *func, uint8_t *seen) {
+  uint8_t f = 0, s = 0;
+  for (int cell = 0; cell < 8; cell++) {
+    uint64_t ones = 0, zeros = 0;
+    for (int v = 0; v < 4; v++) {
+      const uint64_t in_cell = ((cell & 4) ? in1[v] : ~in1[v]) & ((cell & 2) ? in2[v] : ~in2[v])
+          & ((cell & 1) ? in3[v] : ~in3[v]) & mask[v];
+      ones |= in_cell & target[v];
+      zeros |= in_cell & ~target[v];
+    }
+    if (ones != 0 && zeros != 0) return 0;
+    if (ones != 0) f |= (uint8_t)(1u << cell);
+    if ((ones | zeros) != 0) s |= (uint8_t)(1u << cell);
+  }
+  *func = f;
+  *seen = s;
+  return 1;
+}
+
+int sbg_create(sbg_handle **out, int device) {
+  if (out == nullptr) return SBG_ERR_ARG;
+  *out = nullptr;
+  build_host_tables();
+  sbg_handle *h = new sbg_handle();
+  *out = h;  // returned even on failure so the caller can read the error text
+  h->device = device;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    return fail(h, SBG_ERR_CUDA, "no CUDA device available (%s); sboxgates_b200 has no CPU path",
+        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= ndev) return fail(h, SBG_ERR_ARG, "device %d out of range", device);
+  SBG_CUDA(h, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SBG_CUDA(h, cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  SBG_CUDA(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  for (int i = 0; i < 8; i++) SBG_CUDA(h, cudaEventCreate(&h->ev[i]));
+
+  SBG_CUDA(h, cudaMemcpyToSymbol(c_binom, h_binom, sizeof(h_binom)));
+  {
+    // search5: lane = u<<2 | v2, canonical cell bit of slot s is 4-s.
+    uint8_t src5[10][32];
+    for (int k = 0; k < 10; k++) {
+      const int *o = h_rows5[k];
+      for (int lane = 0; lane < 32; lane++) {
+        const int u = lane >> 2, v = lane & 3;
+        int c = 0;
+        c |= ((u >> 2) & 1) << (4 - o[0]);
+        c |= ((u >> 1) & 1) << (4 - o[1]);
+        c |= (u & 1) << (4 - o[2]);
+        c |= ((v >> 1) & 1) << (4 - o[3]);
+        c |= (v & 1) << (4 - o[4]);
+        src5[k][lane] = (uint8_t)c;
+      }
+    }
+    SBG_CUDA(h, cudaMemcpyToSymbol(c_src5, src5, sizeof(src5)));
+
+    // decomp7: group the 70 rows by outer triple; canonical cell bit of slot s (tuple_summary):
+    // a..e -> 4..0, f -> 6, g -> 5.
+    static const int cb[7] = {4, 3, 2, 1, 0, 6, 5};
+    uint32_t src7[25][32];
+    uint8_t first_k[25], nrows[25], row_b[70];
+    int nj = 0;
+    for (int k = 0; k < 70;) {
+      const int *o = h_rows7[k];
+      int rows = 1;
+      while (k + rows < 70 && h_rows7[k + rows][0] == o[0] && h_rows7[k + rows][1] == o[1]
+          && h_rows7[k + rows][2] == o[2]) {
+        rows++;
+      }
+      int rest[4], r = 0;
+      for (int s = 0; s < 7; s++) {
+        if (s != o[0] && s != o[1] && s != o[2]) rest[r++] = s;
+      }
+      for (int i = 0; i < rows; i++) {
+        const int gslot = h_rows7[k + i][6];
+        int m = 0;
+        while (rest[m] != gslot) m++;
+        row_b[k + i] = (uint8_t)(3 - m);
+      }
+      for (int lane = 0; lane < 32; lane++) {
+        const int u0 = lane >> 4, v4 = lane & 15;
+        uint32_t packed = 0;
+        for (int t4 = 0; t4 < 4; t4++) {
+          int c = 0;
+          c |= ((t4 >> 1) & 1) << cb[o[0]];
+          c |= (t4 & 1) << cb[o[1]];
+          c |= u0 << cb[o[2]];
+          for (int m = 0; m < 4; m++) c |= ((v4 >> (3 - m)) & 1) << cb[rest[m]];
+          packed |= (uint32_t)c << (8 * t4);
+        }
+        src7[nj][lane] = packed;
+      }
+      first_k[nj] = (uint8_t)k;
+      nrows[nj] = (uint8_t)rows;
+      nj++;
+      k += rows;
+    }
+    if (nj != 25) return fail(h, SBG_ERR_STATE, "internal: %d outer triples (expected 25)", nj);
+    SBG_CUDA(h, cudaMemcpyToSymbol(c_src7, src7, sizeof(src7)));
+    SBG_CUDA(h, cudaMemcpyToSymbol(c_j_first_k, first_k, sizeof(first_k)));
+    SBG_CUDA(h, cudaMemcpyToSymbol(c_j_rows, nrows, sizeof(nrows)));
+    SBG_CUDA(h, cudaMemcpyToSymbol(c_row_b, row_b, sizeof(row_b)));
+  }
+
+  SBG_CUDA(h, cudaMalloc(&h->d_slots, sizeof(DevProblem) * kSlots));
+  h->d_prob = h->d_slots;
+  h->slots = new sbg_handle::HostProblem[kSlots];
+  SBG_CUDA(h, cudaMallocHost(&h->h_prob, sizeof(DevProblem)));
+  SBG_CUDA(h, cudaMalloc(&h->d_ctl, sizeof(DevCtl)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_ctl, sizeof(DevCtl)));
+  SBG_CUDA(h, cudaMalloc(&h->d_par7, sizeof(DevParams7)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_par7, sizeof(DevParams7)));
+  SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
+  SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
+  const char *cap_env = getenv("SBG_HITS_CAP");
+  h->hits_cap = cap_env != nullptr ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)32 << 20);
+  if (h->hits_cap < 2 * (size_t)SBG_LIST_CAP) h->hits_cap = 2 * (size_t)SBG_LIST_CAP;
+  SBG_CUDA(h, cudaMalloc(&h->d_hits, h->hits_cap * sizeof(uint64_t)));
+  SBG_CUDA(h, cudaMalloc(&h->d_sorted, h->hits_cap * sizeof(uint64_t)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_list, (size_t)SBG_LIST_CAP * sizeof(uint64_t)));
+  h->cub_bytes = 0;
+  SBG_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, h->cub_bytes, h->d_hits, h->d_sorted,
+      (int)h->hits_cap, 0, 63, h->stream));
+  SBG_CUDA(h, cudaMalloc(&h->d_cub, h->cub_bytes));
+  SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  return SBG_OK;
+}
+
+void sbg_destroy(sbg_handle *h) {
+  if (h == nullptr) return;
+  if (h->own_stream != nullptr) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_slots); cudaFreeHost(h->h_prob);
+    cudaFree(h->d_ctl); cudaFreeHost(h->h_ctl);
+    cudaFree(h->d_par7); cudaFreeHost(h->h_par7);
+    cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
+    cudaFree(h->d_hits); cudaFree(h->d_sorted); cudaFree(h->d_cub);
+    cudaFreeHost(h->h_list);
+    for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
+    cudaStreamDestroy(h->own_stream);
+  }
+  delete[] h->slots;
+  delete h;
+}
+
+const char *sbg_last_error(const sbg_handle *h) { return h != nullptr ? h->err : "null handle"; }
+
+int sbg_set_stream(sbg_handle *h, void *cuda_stream) {
+  if (h == nullptr) return SBG_ERR_ARG;
+  h->stream = cuda_stream != nullptr ? (cudaStream_t)cuda_stream : h->own_stream;
+  return SBG_OK;
+}
+
+uint64_t sbg_launch_count(const sbg_handle *h) { return h != nullptr ? h->launches : 0; }
+
+float sbg_last_kernel_ms(const sbg_handle *h, int which) {
+  if (h == nullptr || which < 0 || which > 3) return 0.f;
+  if (which == 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) != cudaSuccess) return 0.f;
+    return ms;
+  }
+  return h->ms[which];
+}
+
+int sbg_use_problem(sbg_handle *h, int slot) {
+  if (h == nullptr) return SBG_ERR_ARG;
+  if (slot < 0 || slot >= kSlots) return fail(h, SBG_ERR_ARG, "slot %d out of range", slot);
+  sbg_handle::HostProblem &hp = h->slots[slot];
+  if (!hp.ready) return fail(h, SBG_ERR_STATE, "slot %d holds no problem", slot);
+  h->d_prob = h->d_slots + slot;
+  h->tables = hp.tables;
+  h->target = hp.target;
+  h->mask = hp.mask;
+  h->n = hp.n;
+  h->nw = hp.nw;
+  h->problem_ready = true;
+  h->list_ready = false;
+  h->list_count = 0;
+  return SBG_OK;
+}
+
+int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
+    const uint64_t *target, const uint64_t *mask, const int8_t *inbits) {
+  if (h == nullptr) return SBG_ERR_ARG;
+  if (slot < 0 || slot >= kSlots) return fail(h, SBG_ERR_ARG, "slot %d out of range", slot);
+  if (tables == nullptr || target == nullptr || mask == nullptr || inbits == nullptr) {
+    return fail(h, SBG_ERR_ARG, "null argument");
+  }
+  if (n < 1 || n > SBG_MAX_GATES) return fail(h, SBG_ERR_ARG, "n = %d out of range", n);
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  // The pinned staging block may still be in flight from the previous upload.
+  SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  sbg_handle::HostProblem &hp = h->slots[slot];
+  memcpy(hp.tables, tables, (size_t)n * 32);
+  memcpy(hp.target, target, 32);
+  memcpy(hp.mask, mask, 32);
+  hp.n = n;
+  const int m = popcount256(mask);
+  hp.nw = m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 4 : 8;
+  hp.ready = true;
+
+  DevProblem *p = h->h_prob;
+  memset(p, 0, sizeof(*p));
+  p->n = n;
+  p->nw = hp.nw;
+  uint32_t cm[8], ct[8], tmp[8];
+  const uint64_t ones[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+  compress_table(ones, mask, cm);
+  compress_table(target, mask, ct);
+  for (int w = 0; w < 8; w++) {
+    p->M[w] = cm[w];
+    p->T[w] = ct[w] & cm[w];
+  }
+  for (int g = 0; g < n; g++) {
+    compress_table(tables + 4 * g, mask, tmp);
+    for (int w = 0; w < 8; w++) p->tabs[w][g] = tmp[w] & cm[w];
+  }
+  uint32_t inmask = 0;
+  for (int k = 0; k < 8 && inbits[k] != -1; k++) {
+    if (inbits[k] >= 0 && inbits[k] < 8) inmask |= 1u << inbits[k];
+  }
+  p->inmask = inmask;
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_slots + slot, p, sizeof(DevProblem), cudaMemcpyHostToDevice,
+      h->stream));
+  return SBG_OK;
+}
+
+int sbg_load_problem(sbg_handle *h, const uint64_t *tables, int n, const uint64_t *target,
+    const uint64_t *mask, const int8_t *inbits) {
+  int rc = sbg_stage_problem(h, 0, tables, n, target, mask, inbits);
+  if (rc != SBG_OK) return rc;
+  return sbg_use_problem(h, 0);
+}
+
+int sbg_search5_part(sbg_handle *h, int part, int nparts, const uint8_t *func_order,
+    uint64_t *key) {
+  if (h == nullptr || key == nullptr) return SBG_ERR_ARG;
+  if (!h->problem_ready) return fail(h, SBG_ERR_STATE, "no problem loaded");
+  if (h->n < 5) return fail(h, SBG_ERR_ARG, "search_5lut needs n >= 5 (lut.c:119)");
+  if (nparts < 1 || part < 0 || part >= nparts) return fail(h, SBG_ERR_ARG, "bad part %d/%d", part, nparts);
+  if (!valid_order(func_order)) return fail(h, SBG_ERR_ARG, "func_order is not a permutation");
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  return run_search5(h, part, nparts, func_order, key);
+}
+
+int sbg_finish5(sbg_handle *h, uint64_t key, const uint8_t *func_order, sbg_result *res) {
+  if (h == nullptr || res == nullptr || func_order == nullptr) return SBG_ERR_ARG;
+  memset(res, 0, sizeof(*res));
+  res->key = key;
+  res->tuples_feasible = h->feasible;
+  res->tuples_swept = h->swept;
+  if (key == SBG_KEY_NONE) return SBG_OK;
+  const uint64_t rank = key >> 12;
+  const int k = (int)((key >> 8) & 0xf);
+  const int pos = (int)(key & 0xff);
+  if (k >= 10 || rank >= h_binom[h->n][5]) return fail(h, SBG_ERR_STATE, "corrupt 5-LUT key");
+  uint16_t comb[5];
+  unrank_combination(rank, h->n, 5, comb);
+  const int *o = h_rows5[k];
+  for (int i = 0; i < 5; i++) res->gates[i] = comb[o[i]];
+  res->found = 1;
+  res->ordering = k;
+  res->pos_outer = pos;
+  res->func_outer = func_order[pos];
+  res->index = rank;
+  uint64_t t_outer[4];
+  sbg_lut_table(res->func_outer, h->tables[res->gates[0]], h->tables[res->gates[1]],
+      h->tables[res->gates[2]], t_outer);
+  if (!sbg_solve_inner(t_outer, h->tables[res->gates[3]], h->tables[res->gates[4]], h->target,
+      h->mask, &res->func_inner, &res->inner_seen)) {
+    return fail(h, SBG_ERR_STATE, "internal: winning 5-LUT key does not decompose");
+  }
+  return SBG_OK;
+}
+
+int sbg_search5(sbg_handle *h, const uint8_t *func_order, sbg_result *res) {
+  uint64_t key = SBG_KEY_NONE;
+  int rc = sbg_search5_part(h, 0, 1, func_order, &key);
+  if (rc != SBG_OK) return rc;
+  return sbg_finish5(h, key, func_order, res);
+}
+
+int sbg_filter7_part(sbg_handle *h, int part, int nparts, uint64_t *list, int *count) {
+  if (h == nullptr || count == nullptr) return SBG_ERR_ARG;
+  if (!h->problem_ready) return fail(h, SBG_ERR_STATE, "no problem loaded");
+  if (h->n < 7) return fail(h, SBG_ERR_ARG, "search_7lut needs n >= 7 (lut.c:259)");
+  if (nparts < 1 || part < 0 || part >= nparts) return fail(h, SBG_ERR_ARG, "bad part %d/%d", part, nparts);
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  uint32_t keep = 0;
+  int rc = run_filter7(h, part, nparts, &keep);
+  if (rc != SBG_OK) return rc;
+  *count = (int)keep;
+  h->list_ready = false;
+  if (list != nullptr && keep > 0) {
+    SBG_CUDA(h, cudaMemcpyAsync(list, h->d_sorted, (size_t)keep * sizeof(uint64_t),
+        cudaMemcpyDeviceToHost, h->stream));
+    SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  // A single part's own sorted list is already installable (sbg_search7 relies on this).
+  h->d_list = h->d_sorted;
+  h->list_count = keep;
+  return SBG_OK;
+}
+
+int sbg_set_list7(sbg_handle *h, const uint64_t *list, int count) {
+  if (h == nullptr || count < 0 || (count > 0 && list == nullptr)) return SBG_ERR_ARG;
+  if ((size_t)count > h->hits_cap) return fail(h, SBG_ERR_ARG, "list of %d entries too long", count);
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  h->list_count = 0;
+  if (count > 0) {
+    SBG_CUDA(h, cudaMemcpyAsync(h->d_hits, list, (size_t)count * sizeof(uint64_t),
+        cudaMemcpyHostToDevice, h->stream));
+    int rc = sort_hits(h, h->d_hits, h->d_sorted, (size_t)count);
+    if (rc != SBG_OK) return rc;
+    SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  h->d_list = h->d_sorted;
+  h->list_count = (uint32_t)std::min<int>(count, SBG_LIST_CAP);
+  h->list_ready = true;
+  return SBG_OK;
+}
+
+int sbg_decomp7_part(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
+    const uint8_t *middle_order, uint64_t *key) {
+  if (h == nullptr || key == nullptr) return SBG_ERR_ARG;
+  if (!h->problem_ready) return fail(h, SBG_ERR_STATE, "no problem loaded");
+  if (!h->list_ready) return fail(h, SBG_ERR_STATE, "no 7-LUT list installed");
+  if (nparts < 1 || part < 0 || part >= nparts) return fail(h, SBG_ERR_ARG, "bad part %d/%d", part, nparts);
+  if (!valid_order(outer_order) || !valid_order(middle_order)) {
+    return fail(h, SBG_ERR_ARG, "function order is not a permutation");
+  }
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  return run_decomp7(h, part, nparts, outer_order, middle_order, key);
+}
+
+int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
+    const uint8_t *middle_order, sbg_result *res) {
+  if (h == nullptr || res == nullptr || outer_order == nullptr || middle_order == nullptr) {
+    return SBG_ERR_ARG;
+  }
+  memset(res, 0, sizeof(*res));
+  res->key = key;
+  res->tuples_feasible = h->list_count;
+  res->tuples_swept = h->swept;
+  if (key == SBG_KEY_NONE) return SBG_OK;
+  const uint64_t idx = key >> 23;
+  const int k = (int)((key >> 16) & 0x7f);
+  const int po = (int)((key >> 8) & 0xff);
+  const int pm = (int)(key & 0xff);
+  if (idx >= h->list_count || k >= 70) return fail(h, SBG_ERR_STATE, "corrupt 7-LUT key");
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  uint64_t pair[2] = {0, 0};
+  const size_t first = idx > 0 ? idx - 1 : 0;
+  SBG_CUDA(h, cudaMemcpyAsync(pair, h->d_list + first, (idx > 0 ? 2 : 1) * sizeof(uint64_t),
+      cudaMemcpyDeviceToHost, h->stream));
+  SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  const uint64_t cur = idx > 0 ? pair[1] : pair[0];
+  uint16_t t[7];
+  for (int i = 0; i < 7; i++) t[i] = (uint16_t)((cur >> (9 * (6 - i))) & 0x1ff);
+  const int *o = h_rows7[k];
+  for (int i = 0; i < 7; i++) res->gates[i] = t[o[i]];
+  res->found = 1;
+  res->ordering = k;
+  res->pos_outer = po;
+  res->pos_middle = pm;
+  res->func_outer = outer_order[po];
+  res->func_middle = middle_order[pm];
+  res->index = idx;
+  // lut.c:432-435 quirk (see k_decomp7): rows 0-3 may have been evaluated with the previous
+  // tuple's outer tables; the solved inner function must come from the same tables.
+  uint16_t outer_a = res->gates[0];
+  if (idx > 0 && k < 4 && t[0] == 0) {
+    const uint64_t prev = pair[0];
+    if ((uint16_t)((prev >> 9) & 0x1ff) == t[1] && (uint16_t)(prev & 0x1ff) == t[2]) {
+      outer_a = (uint16_t)((prev >> 45) & 0x1ff);
+      res->stale_outer = 1;
+    }
+  }
+  uint64_t t_outer[4], t_middle[4];
+  sbg_lut_table(res->func_outer, h->tables[outer_a], h->tables[res->gates[1]],
+      h->tables[res->gates[2]], t_outer);
+  sbg_lut_table(res->func_middle, h->tables[res->gates[3]], h->tables[res->gates[4]],
+      h->tables[res->gates[5]], t_middle);
+  if (!sbg_solve_inner(t_outer, t_middle, h->tables[res->gates[6]], h->target, h->mask,
+      &res->func_inner, &res->inner_seen)) {
+    return fail(h, SBG_ERR_STATE, "internal: winning 7-LUT key does not decompose");
+  }
+  return SBG_OK;
+}
+
+int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle_order,
+    sbg_result *res) {
+  if (h == nullptr || res == nullptr) return SBG_ERR_ARG;
+  int count = 0;
+  int rc = sbg_filter7_part(h, 0, 1, nullptr, &count);
+  if (rc != SBG_OK) return rc;
+  h->list_ready = true;  // the device-resident sorted list of the only part is the list
+  uint64_t key = SBG_KEY_NONE;
+  rc = sbg_decomp7_part(h, 0, 1, outer_order, middle_order, &key);
+  if (rc != SBG_OK) return rc;
+  return sbg_finish7(h, key, outer_order, middle_order, res);
+}
+
+}  // extern "C"

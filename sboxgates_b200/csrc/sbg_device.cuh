@@ -1,0 +1,590 @@
+// sbg_device.cuh -- device-side data layout and kernels of the B200 3-LUT search.
+//
+// Everything here is integer/bitwise work on 256-bit truth tables (no tensor cores: there is no
+// contraction to map to them).  The reference functions being replaced are lut.c:34-66
+// (check_n_lut_possible), lut.c:79-109 (get_lut_function), lut.c:116-249 (search_5lut) and
+// lut.c:256-487 (search_7lut); see DESIGN.md for how the loops were restructured.
+//
+// Data layout in HBM (DevProblem, 16.5 KB, uploaded once per search state):
+//   * tables are compressed to the masked positions only: bit i of a compressed table is the
+//     table's value at the i-th set position of the mask, so a search under a mask of popcount m
+//     touches NW = ceil(m/32) words per table instead of 8 (every test in the reference is
+//     "under the mask", lut.c:38-42,86, so positions outside it never matter);
+//   * word-major (tabs[w][gate]) so that a warp whose lanes hold different gates reads
+//     consecutive shared-memory banks.
+// Kernels stage the tables into shared memory with cp.async (LDGSTS) and keep them there; the
+// per-launch DRAM traffic is the 16.5 KB problem block plus the hit list.
+#pragma once
+
+#include <cuda_pipeline.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sbg {
+
+constexpr int kMaxGatesPad = 512;
+constexpr int kThreads = 256;
+constexpr int kWarpsPerCta = kThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct DevProblem {
+  uint32_t tabs[8][kMaxGatesPad];  // [word][gate], compressed + pre-ANDed with the mask
+  uint32_t T[8];                   // target & mask, compressed
+  uint32_t M[8];                   // compressed mask = low popcount(mask) bits set
+  int32_t n;                       // number of gates
+  int32_t nw;                      // words in use: 1, 2, 4 or 8
+  uint32_t inmask;                 // bit g set: gate g (< 8) is excluded (lut.c:177-185)
+  int32_t pad;
+};
+
+struct DevCtl {
+  unsigned long long ticket;       // next work item
+  unsigned long long best;         // minimum key found so far
+  unsigned long long stop_ticket;  // search5: tickets above this cannot improve `best`
+  unsigned long long hit_count;    // filter7: feasible tuples appended
+  unsigned long long swept;        // tuples put through the feasibility test
+  unsigned long long feasible;     // search5: feasible tuples met
+  unsigned int overflow;           // filter7: hit buffer too small
+  unsigned int pad;
+};
+
+// Per-call parameters of the 7-LUT decomposition: where each outer function sits in the shuffled
+// outer order, and for the shuffled middle order the 256-bit sets
+//   lo[s*16+a] = { pm : (middle_order[pm] & 0x0f & s) == a },  hi[...] likewise for the high nibble,
+// from which { pm : (middle_order[pm] & S) == A } = lo[S&15, A&15] & hi[S>>4, A>>4].
+struct DevParams7 {
+  uint32_t lo[256][8];
+  uint32_t hi[256][8];
+  uint8_t pos_outer[256];
+};
+
+__constant__ uint64_t c_binom[501][8];   // C(m, r), 0 <= m <= 500, 0 <= r <= 7
+__constant__ uint8_t c_src5[10][32];     // search5: ordering k, lane (u,v2) -> canonical cell
+__constant__ uint32_t c_src7[25][32];    // decomp7: outer triple j, lane (u0,v4) -> 4 cells (u2,u1)
+__constant__ uint8_t c_j_first_k[25];    // first ordering row of outer triple j
+__constant__ uint8_t c_j_rows[25];       // rows sharing that outer triple (4 or 1)
+__constant__ uint8_t c_row_b[70];        // bit of v4 that is the g input in ordering row k
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// Stages `rows` rows of `npad` words of the problem's tables into shared memory with cp.async.
+__device__ __forceinline__ void stage_tables(uint32_t *s_tabs, const DevProblem *prob, int rows,
+    int npad) {
+  const int chunks_per_row = npad >> 2;  // 16-byte chunks
+  for (int i = threadIdx.x; i < rows * chunks_per_row; i += blockDim.x) {
+    const int w = i / chunks_per_row;
+    const int c = i - w * chunks_per_row;
+    __pipeline_memcpy_async(s_tabs + w * npad + 4 * c, &prob->tabs[w][4 * c], 16);
+  }
+  __pipeline_commit();
+  __pipeline_wait_prior(0);
+  __syncthreads();
+}
+
+// Work item t of the P-element prefixes of K-combinations over n gates, lexicographic order.
+// Also returns the rank (in C(n,K) order, lut.c:635-662) of the first combination with that prefix.
+template <int P, int K>
+__device__ __forceinline__ void unrank_prefix(uint64_t t, int n, int *pre, uint64_t &base_rank) {
+  const int np = n - (K - P);
+  int x = 0;
+  base_rank = 0;
+#pragma unroll
+  for (int pos = 0; pos < P; pos++) {
+    for (;; x++) {
+      const uint64_t cnt = c_binom[np - x - 1][P - pos - 1];
+      if (t < cnt) break;
+      t -= cnt;
+      base_rank += c_binom[n - x - 1][K - pos - 1];
+    }
+    pre[pos] = x++;
+  }
+}
+
+// q-th pair (i < j) of {0..r-1} in lexicographic order.
+__device__ __forceinline__ void unrank_pair(uint32_t q, int r, int &i, int &j) {
+  const float b = 2.0f * r - 1.0f;
+  int ii = (int)((b - sqrtf(fmaxf(b * b - 8.0f * (float)q, 0.0f))) * 0.5f);
+  ii = max(0, min(ii, r - 2));
+  // offset(i) = i*(2r-i-1)/2 pairs precede row i
+  while (ii > 0 && (uint32_t)(ii * (2 * r - ii - 1) / 2) > q) ii--;
+  while ((uint32_t)((ii + 1) * (2 * r - ii - 2) / 2) <= q) ii++;
+  i = ii;
+  j = ii + 1 + (int)(q - (uint32_t)(ii * (2 * r - ii - 1) / 2));
+}
+
+__device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
+  return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sweep kernel.  One warp per P-element prefix; lanes take the (f,g) pairs that complete it.
+//   P = 3 (K = 5): search_5lut's loop over C(n,5) (lut.c:174-245), feasibility test and the
+//                  10 x 256 decomposition attempts fused; result = minimum key in ctl->best.
+//   P = 5 (K = 7): phase 1 of search_7lut (lut.c:294-327); result = unordered list of feasible
+//                  combinations (packed 9 bits per gate), sorted afterwards.
+//
+// Feasibility (lut.c:34-66) of prefix + (f,g): no cell of the 2^K-cell partition may hold both a
+// masked 1 and a masked 0 of the target.  A prefix cell that is already pure stays pure however it
+// is split, so only the "mixed" prefix cells are kept (their ones C1 = C & T and zeros C0 = C & ~T,
+// in shared memory); each must be split by f and g into four parts none of which meets both C1 and
+// C0.  A pair is dropped at the first cell it fails on.
+template <int NW, int P>
+__global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
+    unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap) {
+  constexpr int K = P + 2;
+  constexpr int NC = 1 << P;
+  extern __shared__ uint32_t smem[];
+  __shared__ uint8_t s_pos[256];
+
+  const int n = prob->n;
+  const int npad = (n + 3) & ~3;
+  uint32_t *s_tabs = smem;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t *cells = smem + NW * npad + warp * (NC * 2 * NW);  // per mixed cell: C1[NW], C0[NW]
+
+  if constexpr (P == 3) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
+  }
+  stage_tables(s_tabs, prob, NW, npad);
+
+  uint32_t T[NW], M[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    T[w] = prob->T[w];
+    M[w] = prob->M[w];
+  }
+  const uint32_t inmask = prob->inmask;
+  const uint64_t total = c_binom[n - 2][P];
+
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) {
+      bool stop = false;
+      if (P == 5) stop = volatile_load(&ctl->hit_count) >= list_cap;
+      t = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+    }
+    t = __shfl_sync(kFull, t, 0);
+    if (t == ~0ull) break;
+    const uint64_t gt = t * (uint64_t)nparts + (uint64_t)part;
+    if (gt >= total) break;
+    if (P == 3 && gt > volatile_load(&ctl->stop_ticket)) break;
+
+    int pre[P];
+    uint64_t base_rank;
+    unrank_prefix<P, K>(gt, n, pre, base_rank);
+    bool rejected = false;
+#pragma unroll
+    for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
+    if (rejected) continue;
+    const int last = pre[P - 1];
+    const int r = n - last - 1;
+    const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
+
+    // Prefix cells: lane = cell index, first prefix gate = most significant bit (lut.c:46-49).
+    uint32_t mixed_ballot;
+    {
+      uint32_t c1[NW], c0[NW];
+      uint32_t ones = 0, zeros = 0;
+      const int cell = lane & (NC - 1);
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        uint32_t tt = M[w];
+#pragma unroll
+        for (int i = 0; i < P; i++) {
+          const uint32_t tv = s_tabs[w * npad + pre[i]];
+          tt &= ((cell >> (P - 1 - i)) & 1) ? tv : ~tv;
+        }
+        c1[w] = tt & T[w];
+        c0[w] = tt & ~T[w];
+        ones |= c1[w];
+        zeros |= c0[w];
+      }
+      const bool mixed = (lane < NC) && ones != 0 && zeros != 0;
+      mixed_ballot = __ballot_sync(kFull, mixed);
+      __syncwarp();
+      if (mixed) {
+        const int slot = __popc(mixed_ballot & lanemask_lt());
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+          cells[slot * 2 * NW + w] = c1[w];
+          cells[slot * 2 * NW + NW + w] = c0[w];
+        }
+      }
+      __syncwarp();
+    }
+    const int mc = __popc(mixed_ballot);
+
+    bool warp_done = false;
+    unsigned long long emitted = 0;
+    for (uint32_t q0 = 0; q0 < Q && !warp_done; q0 += 32) {
+      const uint32_t q = q0 + lane;
+      bool alive = q < Q;
+      int pi, pj;
+      unrank_pair(alive ? q : 0u, r, pi, pj);
+      const int gf = last + 1 + pi;
+      const int gg = last + 1 + pj;
+      if ((gf < 8 && ((inmask >> gf) & 1u)) || (gg < 8 && ((inmask >> gg) & 1u))) alive = false;
+
+      if (mc > 0) {
+        uint32_t m11[NW], m10[NW], m01[NW], m00[NW];  // the four (f,g) minterms
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+          const uint32_t tf = s_tabs[w * npad + gf];
+          const uint32_t tg = s_tabs[w * npad + gg];
+          m11[w] = tf & tg;
+          m10[w] = tf & ~tg;
+          m01[w] = ~tf & tg;
+          m00[w] = ~(tf | tg);
+        }
+        for (int cj = 0; cj < mc; cj++) {
+          if (!__any_sync(kFull, alive)) break;
+          uint32_t a11 = 0, a10 = 0, a01 = 0, a00 = 0, b11 = 0, b10 = 0, b01 = 0, b00 = 0;
+#pragma unroll
+          for (int w = 0; w < NW; w++) {
+            const uint32_t c1 = cells[cj * 2 * NW + w];
+            const uint32_t c0 = cells[cj * 2 * NW + NW + w];
+            a11 |= c1 & m11[w]; b11 |= c0 & m11[w];
+            a10 |= c1 & m10[w]; b10 |= c0 & m10[w];
+            a01 |= c1 & m01[w]; b01 |= c0 & m01[w];
+            a00 |= c1 & m00[w]; b00 |= c0 & m00[w];
+          }
+          if ((a11 != 0 && b11 != 0) || (a10 != 0 && b10 != 0) || (a01 != 0 && b01 != 0)
+              || (a00 != 0 && b00 != 0)) {
+            alive = false;
+          }
+        }
+      }
+
+      uint32_t fb = __ballot_sync(kFull, alive);
+      if (fb == 0) continue;
+
+      if constexpr (P == 5) {
+        const int cnt = __popc(fb);
+        unsigned long long base_slot = 0;
+        if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)cnt);
+        base_slot = __shfl_sync(kFull, base_slot, 0);
+        if (alive) {
+          const unsigned long long slot = base_slot + __popc(fb & lanemask_lt());
+          uint64_t packed = 0;
+#pragma unroll
+          for (int i = 0; i < P; i++) packed = (packed << 9) | (uint64_t)pre[i];
+          packed = (packed << 18) | ((uint64_t)gf << 9) | (uint64_t)gg;
+          if (slot < hits_cap) {
+            hits[slot] = packed;
+          } else {
+            atomicExch(&ctl->overflow, 1u);
+          }
+        }
+        // A single prefix never needs to contribute more than the list cap (lut.c:316-318).
+        emitted += cnt;
+        if (emitted >= list_cap) warp_done = true;
+      } else {
+        // search_5lut: try the 10 orderings x 256 outer functions on each feasible tuple
+        // (lut.c:189-230) using only its 32-cell summary H1/H0 (cells that contain a masked
+        // 1 / a masked 0 of the target).
+        while (fb != 0 && !warp_done) {
+          const int src = __ffs(fb) - 1;
+          fb &= fb - 1;
+          const int gd = __shfl_sync(kFull, gf, src);
+          const int ge = __shfl_sync(kFull, gg, src);
+          uint32_t ones = 0, zeros = 0;
+#pragma unroll
+          for (int w = 0; w < NW; w++) {
+            uint32_t tt = M[w];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              const uint32_t tv = s_tabs[w * npad + pre[i]];
+              tt &= ((lane >> (4 - i)) & 1) ? tv : ~tv;
+            }
+            const uint32_t td = s_tabs[w * npad + gd];
+            const uint32_t te = s_tabs[w * npad + ge];
+            tt &= ((lane >> 1) & 1) ? td : ~td;
+            tt &= (lane & 1) ? te : ~te;
+            ones |= tt & T[w];
+            zeros |= tt & ~T[w];
+          }
+          const uint32_t H1 = __ballot_sync(kFull, ones != 0);
+          const uint32_t H0 = __ballot_sync(kFull, zeros != 0);
+          if (lane == 0) atomicAdd(&ctl->feasible, 1ull);
+
+          for (int k = 0; k < 10; k++) {
+            const int s = c_src5[k][lane];
+            const uint32_t b1 = __ballot_sync(kFull, (H1 >> s) & 1u);
+            const uint32_t b0 = __ballot_sync(kFull, (H0 >> s) & 1u);
+            // wv(u): bits 0-3 = inner cells (x, d, e) with a masked 1 contributed by outer
+            // pattern u, bits 4-7 = the same for masked 0.
+#define SBG_W5(u) (((b1 >> (4 * (u))) & 0xfu) | (((b0 >> (4 * (u))) & 0xfu) << 4))
+            uint32_t L = 0;
+#pragma unroll
+            for (int u = 0; u < 5; u++) {
+              if ((lane >> u) & 1) L |= SBG_W5(u);
+            }
+            uint32_t ok[8];
+#pragma unroll
+            for (int hi = 0; hi < 8; hi++) {
+              uint32_t rr = L;
+              if (hi & 1) rr |= SBG_W5(5);
+              if (hi & 2) rr |= SBG_W5(6);
+              if (hi & 4) rr |= SBG_W5(7);
+              ok[hi] = __ballot_sync(kFull, ((rr & (rr >> 4)) & 0xfu) == 0);
+            }
+#undef SBG_W5
+            // Outer function fo = hi*32+lane maps pattern u to x = bit u of fo; it works iff
+            // neither {u: x=1} nor {u: x=0} merges a masked 1 and a masked 0 into one inner cell.
+            uint32_t best_pos = 256;
+#pragma unroll
+            for (int hi = 0; hi < 8; hi++) {
+              const uint32_t surv = ok[hi] & __brev(ok[7 - hi]);
+              if ((surv >> lane) & 1u) best_pos = min(best_pos, (uint32_t)s_pos[hi * 32 + lane]);
+            }
+            best_pos = __reduce_min_sync(kFull, best_pos);
+            if (best_pos < 256) {
+              const uint64_t key = ((base_rank + q0 + src) << 12) | ((uint64_t)k << 8) | best_pos;
+              if (lane == 0) {
+                atomicMin(&ctl->best, (unsigned long long)key);
+                atomicMin(&ctl->stop_ticket, (unsigned long long)gt);
+              }
+              warp_done = true;
+              break;
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) atomicAdd(&ctl->swept, (unsigned long long)Q);
+    if (P == 3 && warp_done) break;  // every later ticket of this warp has a larger key
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 2 of search_7lut (lut.c:416-484): one warp per feasible 7-tuple.
+
+__device__ __forceinline__ uint32_t compress16(uint32_t r16, int b, int z) {
+  // Keeps the 8 bits of a 16-bit set over v4 whose index has bit b equal to z, in order.
+  uint32_t t;
+  switch (b) {
+    case 3:
+      return (r16 >> (8 * z)) & 0xffu;
+    case 2:
+      t = r16 >> (4 * z);
+      return (t & 0x0fu) | ((t >> 4) & 0xf0u);
+    case 1:
+      t = r16 >> (2 * z);
+      return (t & 0x03u) | ((t >> 2) & 0x0cu) | ((t >> 4) & 0x30u) | ((t >> 6) & 0xc0u);
+    default:
+      t = (r16 >> z) & 0x5555u;
+      t = (t | (t >> 1)) & 0x3333u;
+      t = (t | (t >> 2)) & 0x0f0fu;
+      return (t | (t >> 4)) & 0xffu;
+  }
+}
+
+// 128-cell summary of a 7-tuple: word fg (= f<<1|g) bit l (= a<<4|b<<3|c<<2|d<<1|e) of H1 / H0 is
+// set iff the cell holds a masked position with target 1 / 0.  Written to sH[0..3] / sH[4..7].
+template <int NW>
+__device__ __forceinline__ void tuple_summary(const uint32_t *s_tabs, int npad, const int *g,
+    const uint32_t *T, const uint32_t *M, int lane, uint32_t *sH) {
+  uint32_t h1[4] = {0, 0, 0, 0}, h0[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    uint32_t tt = M[w];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const uint32_t tv = s_tabs[w * npad + g[i]];
+      tt &= ((lane >> (4 - i)) & 1) ? tv : ~tv;
+    }
+    const uint32_t tf = s_tabs[w * npad + g[5]];
+    const uint32_t tg = s_tabs[w * npad + g[6]];
+    const uint32_t s3 = tt & tf & tg, s2 = tt & tf & ~tg, s1 = tt & ~tf & tg, s0 = tt & ~tf & ~tg;
+    h1[0] |= s0 & T[w]; h0[0] |= s0 & ~T[w];
+    h1[1] |= s1 & T[w]; h0[1] |= s1 & ~T[w];
+    h1[2] |= s2 & T[w]; h0[2] |= s2 & ~T[w];
+    h1[3] |= s3 & T[w]; h0[3] |= s3 & ~T[w];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint32_t b1 = __ballot_sync(kFull, h1[j] != 0);
+    const uint32_t b0 = __ballot_sync(kFull, h0[j] != 0);
+    if (lane == 0) {
+      sH[j] = b1;
+      sH[4 + j] = b0;
+    }
+  }
+  __syncwarp();
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, const DevParams7 *__restrict__ par, const uint64_t *__restrict__ list,
+    unsigned int count, int part, int nparts) {
+  extern __shared__ uint32_t smem[];
+  __shared__ uint32_t s_lo[256 * 8];
+  __shared__ uint32_t s_hi[256 * 8];
+  __shared__ uint8_t s_pos[256];
+  __shared__ uint32_t s_H[kWarpsPerCta][24];
+
+  const int n = prob->n;
+  const int npad = (n + 3) & ~3;
+  uint32_t *s_tabs = smem;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+
+  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+    s_lo[i] = (&par->lo[0][0])[i];
+    s_hi[i] = (&par->hi[0][0])[i];
+  }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = par->pos_outer[i];
+  stage_tables(s_tabs, prob, NW, npad);
+
+  uint32_t T[NW], M[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    T[w] = prob->T[w];
+    M[w] = prob->M[w];
+  }
+  uint32_t *sH = s_H[warp];
+
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(&ctl->ticket, 1ull);
+    t = __shfl_sync(kFull, t, 0);
+    const uint64_t idx = t * (uint64_t)nparts + (uint64_t)part;
+    if (idx >= count) break;
+    if ((volatile_load(&ctl->best) >> 23) < idx) break;  // a smaller list index already matched
+
+    const uint64_t cur = list[idx];
+    int g[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) g[i] = (int)((cur >> (9 * (6 - i))) & 0x1ffu);
+
+    // The reference's outer-table cache is keyed by a truncated value (lut.c:379,432-435): rows
+    // 0-3 of a tuple whose first gate is 0 reuse the previous tuple's last outer tables when that
+    // tuple ended in the same two gates this one continues with.  Reproduce it: those rows see
+    // gate prev[1] in place of gate 0.
+    bool stale = false;
+    int sub = 0;
+    if (idx > 0) {
+      const uint64_t prev = list[idx - 1];
+      stale = g[0] == 0 && (int)((prev >> 9) & 0x1ffu) == g[1] && (int)(prev & 0x1ffu) == g[2];
+      sub = (int)((prev >> 45) & 0x1ffu);
+    }
+    tuple_summary<NW>(s_tabs, npad, g, T, M, lane, sH);
+    if (stale) {
+      int g2[7];
+#pragma unroll
+      for (int i = 0; i < 7; i++) g2[i] = g[i];
+      g2[0] = sub;
+      tuple_summary<NW>(s_tabs, npad, g2, T, M, lane, sH + 8);
+    }
+
+    bool found = false;
+    uint64_t key = 0;
+    for (int j = 0; j < 25 && !found; j++) {
+      const uint32_t *Hs = (stale && j == 0) ? sH + 8 : sH;
+      const uint32_t srcw = c_src7[j][lane];
+      uint32_t P1[4], P0[4];
+#pragma unroll
+      for (int t4 = 0; t4 < 4; t4++) {
+        const uint32_t c = (srcw >> (8 * t4)) & 0x7fu;
+        P1[t4] = __ballot_sync(kFull, (Hs[c >> 5] >> (c & 31u)) & 1u);
+        P0[t4] = __ballot_sync(kFull, (Hs[4 + (c >> 5)] >> (c & 31u)) & 1u);
+      }
+      // W[u]: low half = the 16 cells (over the four non-outer gates) in which outer pattern u
+      // holds a masked 1, high half = the same for a masked 0.
+      uint32_t W[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        W[u] = ((P1[u >> 1] >> (16 * (u & 1))) & 0xffffu)
+            | (((P0[u >> 1] >> (16 * (u & 1))) & 0xffffu) << 16);
+      }
+      uint32_t L = 0;
+#pragma unroll
+      for (int u = 0; u < 5; u++) {
+        if ((lane >> u) & 1) L |= W[u];
+      }
+      uint32_t ok[8];
+#pragma unroll
+      for (int hi = 0; hi < 8; hi++) {
+        uint32_t rr = L;
+        if (hi & 1) rr |= W[5];
+        if (hi & 2) rr |= W[6];
+        if (hi & 4) rr |= W[7];
+        ok[hi] = __ballot_sync(kFull, ((rr & (rr >> 16)) & 0xffffu) == 0);
+      }
+      uint32_t any = 0;
+      uint32_t my_surv = 0;
+#pragma unroll
+      for (int hi = 0; hi < 8; hi++) {
+        const uint32_t sv = ok[hi] & __brev(ok[7 - hi]);
+        any |= sv;
+        if (lane == hi) my_surv = sv;
+      }
+      if (any == 0) continue;  // no outer function leaves a conflict-free 5-input remainder
+      uint32_t *surv = sH + 16;
+      __syncwarp();
+      if (lane < 8) surv[lane] = my_surv;
+      __syncwarp();
+
+      const int k0 = c_j_first_k[j];
+      const int nrows = c_j_rows[j];
+      for (int row = 0; row < nrows && !found; row++) {
+        const int k = k0 + row;
+        const int b = c_row_b[k];
+        uint32_t best_local = 0xffffffffu;
+        for (int hi = 0; hi < 8; hi++) {
+          uint32_t s = surv[hi];
+          while (s != 0) {
+            const int lb = __ffs(s) - 1;
+            s &= s - 1;
+            const int fo = hi * 32 + lb;
+            uint32_t r1 = 0, r0 = 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              if ((fo >> u) & 1) r1 |= W[u]; else r0 |= W[u];
+            }
+            // Lane = (constraint ci = (x, z), word w of the 256-bit set over middle positions).
+            const int ci = lane >> 3;
+            const int w = lane & 7;
+            const uint32_t R = (ci & 2) ? r1 : r0;
+            const uint32_t A = compress16(R & 0xffffu, b, ci & 1);
+            const uint32_t B = compress16(R >> 16, b, ci & 1);
+            uint32_t m = 0xffffffffu;
+            if (A != 0 && B != 0) {
+              // fm must send the v's of A to one value and those of B to the other.
+              const uint32_t S = A | B;
+              const uint32_t sl = (S & 15u) * 16u, sh = (S >> 4) * 16u;
+              m = (s_lo[(sl + (A & 15u)) * 8 + w] & s_hi[(sh + (A >> 4)) * 8 + w])
+                  | (s_lo[(sl + (B & 15u)) * 8 + w] & s_hi[(sh + (B >> 4)) * 8 + w]);
+            }
+            m &= __shfl_xor_sync(kFull, m, 8);
+            m &= __shfl_xor_sync(kFull, m, 16);
+            const uint32_t nz = __ballot_sync(kFull, m != 0) & 0xffu;
+            if (nz != 0) {
+              const int w0 = __ffs(nz) - 1;
+              const uint32_t mw = __shfl_sync(kFull, m, w0);
+              const uint32_t pm = (uint32_t)w0 * 32u + (uint32_t)(__ffs(mw) - 1);
+              best_local = min(best_local, ((uint32_t)s_pos[fo] << 8) | pm);
+            }
+          }
+        }
+        if (best_local != 0xffffffffu) {
+          key = (idx << 23) | ((uint64_t)k << 16) | best_local;
+          found = true;
+        }
+      }
+    }
+    if (found) {
+      if (lane == 0) atomicMin(&ctl->best, (unsigned long long)key);
+      break;  // later tickets of this warp have larger list indices
+    }
+  }
+}
+
+}  // namespace sbg

@@ -1,0 +1,92 @@
+"""Multi-GPU search: one process per GPU, `torch.distributed` for the plumbing.
+
+The reference parallelises search_5lut / search_7lut over MPI ranks with a master/worker protocol
+(lut.c:137-159, 212-238, 329-360, 463-482, 664-740; sboxgates.c:619-642): contiguous slices of the
+combination space, first finder wins.  Here every rank runs the same host program with the same
+RNG state, takes an interleaved share of the work items, and the ranks agree on the answer with
+  * search_5lut: one all-reduce(MIN) of the 64-bit key (rank of combination, ordering, position);
+  * search_7lut: one all-gather of the per-rank hit lists (phase 1, lut.c:329-349), then one
+    all-reduce(MIN) of the key (list index, ordering, outer position, middle position).
+Because the key orders candidates exactly as the reference's single-rank loop visits them, the
+result is the reference's size == 1 result for any number of GPUs.
+
+The engine is any object with the `LutEngine` part-methods; the CPU tests drive this module over
+`gloo` with an oracle-backed stand-in engine, the product uses `LutEngine` (CUDA) over `nccl`.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .lut import (SBG_KEY_NONE, SBG_LIST_CAP, result5_to_ret, result7_to_ret, shuffled_order,
+                  shuffled_orders7)
+
+_I64_MAX = (1 << 63) - 1
+
+
+def _key_to_i64(key):
+    # Keys use < 2^63 except the "none" sentinel, which maps to int64 max (still the maximum).
+    return _I64_MAX if key == SBG_KEY_NONE else int(key)
+
+
+def _i64_to_key(v):
+    return SBG_KEY_NONE if v == _I64_MAX else int(v)
+
+
+class DistributedLutSearch:
+    def __init__(self, engine, group=None, device=None):
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        backend = dist.get_backend(group)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" \
+                else torch.device("cpu")
+        self.device = device
+        self.collectives = 0
+
+    # -- collectives ---------------------------------------------------------------------------
+    def _allreduce_min_key(self, key):
+        t = torch.tensor([_key_to_i64(key)], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        self.collectives += 1
+        return _i64_to_key(int(t.item()))
+
+    def _allgather_lists(self, local):
+        """local: sorted uint64 array (<= SBG_LIST_CAP).  Returns the concatenation over ranks."""
+        cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
+        counts = [torch.zeros_like(cnt) for _ in range(self.world)]
+        dist.all_gather(counts, cnt, group=self.group)
+        counts = [int(c.item()) for c in counts]
+        width = max(counts)
+        self.collectives += 1
+        if width == 0:
+            return np.zeros(0, dtype=np.uint64)
+        buf = torch.zeros(width, dtype=torch.int64)
+        buf[:local.shape[0]] = torch.from_numpy(local.view(np.int64))
+        buf = buf.to(self.device)
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        dist.all_gather(parts, buf, group=self.group)
+        self.collectives += 1
+        out = [p[:c].cpu().numpy().view(np.uint64) for p, c in zip(parts, counts)]
+        return np.concatenate(out)
+
+    # -- searches ------------------------------------------------------------------------------
+    def search_5lut(self, tables, target, mask, inbits, rng):
+        order = shuffled_order(rng)
+        self.engine.load(tables, target, mask, inbits)
+        key = self.engine.search5_part(self.rank, self.world, order)
+        key = self._allreduce_min_key(key)
+        return result5_to_ret(self.engine.finish5(key, order), rng)
+
+    def search_7lut(self, tables, target, mask, inbits, rng):
+        outer, middle = shuffled_orders7(rng)
+        self.engine.load(tables, target, mask, inbits)
+        local = self.engine.filter7_part(self.rank, self.world)
+        merged = self._allgather_lists(local)
+        # Every rank installs the same merged list; set_list7 sorts it and keeps the first
+        # SBG_LIST_CAP entries (lut.c:316-318 at size == 1).
+        self.engine.set_list7(merged)
+        key = self.engine.decomp7_part(self.rank, self.world, outer, middle)
+        key = self._allreduce_min_key(key)
+        return result7_to_ret(self.engine.finish7(key, outer, middle), rng)

@@ -49,7 +49,8 @@ class OrcRng(C.Structure):
 
 class OrcStats(C.Structure):
     _fields_ = [("tuples_filtered", C.c_uint64), ("tuples_feasible", C.c_uint64),
-                ("candidates", C.c_uint64), ("stale_cache_rows", C.c_uint64)]
+                ("candidates", C.c_uint64), ("stale_cache_rows", C.c_uint64),
+                ("stale_hit", C.c_uint64)]
 
 
 def _u64(a):
@@ -93,6 +94,10 @@ def oracle_lib():
                                        C.POINTER(OrcStats)]
     lib.orc_filter_7lut.argtypes = [u64p, C.c_int, u64p, u64p, i8p, u16p, C.c_int,
                                     C.POINTER(OrcStats)]
+    lib.orc_search5_key.restype = C.c_uint64
+    lib.orc_search5_key.argtypes = [u64p, C.c_int, u64p, u64p, i8p, u8p, C.c_int, C.c_int]
+    lib.orc_decomp7_key.restype = C.c_uint64
+    lib.orc_decomp7_key.argtypes = [u64p, u64p, u64p, u16p, C.c_int, u8p, u8p, C.c_int, C.c_int]
     lib.orc_order7_row.argtypes = [C.c_int, C.POINTER(C.c_int)]
     lib.orc_order5_row.argtypes = [C.c_int, C.POINTER(C.c_int)]
     _oracle = lib
@@ -125,6 +130,31 @@ def oracle_filter7(tables, target, mask, inbits, cap=100000):
     cnt = lib.orc_filter_7lut(tp, tables.shape[0], gp, mp, ib.ctypes.data_as(i8p),
                               out.ctypes.data_as(u16p), cap, C.byref(stats))
     return out[:cnt].copy(), stats
+
+
+def _order(order):
+    return (C.c_uint8 * 256).from_buffer_copy(bytes(order))
+
+
+def oracle_search5_key(tables, target, mask, inbits, func_order, part=0, nparts=1):
+    lib = oracle_lib()
+    tables, tp = _u64(tables)
+    target, gp = _u64(target)
+    mask, mp = _u64(mask)
+    ib = inbits_array(inbits)
+    return int(lib.orc_search5_key(tp, tables.shape[0], gp, mp, ib.ctypes.data_as(i8p),
+                                   _order(func_order), part, nparts))
+
+
+def oracle_decomp7_key(tables, target, mask, tuples, outer, middle, part=0, nparts=1):
+    """tuples: (count, 7) uint16 array = the feasible list in lexicographic order."""
+    lib = oracle_lib()
+    tables, tp = _u64(tables)
+    target, gp = _u64(target)
+    mask, mp = _u64(mask)
+    lst = np.ascontiguousarray(tuples, dtype=np.uint16).reshape(-1, 7)
+    return int(lib.orc_decomp7_key(tp, gp, mp, lst.ctypes.data_as(u16p), lst.shape[0],
+                                   _order(outer), _order(middle), part, nparts))
 
 
 def order7_rows():

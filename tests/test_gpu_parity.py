@@ -1,0 +1,152 @@
+"""GPU: the CUDA path (through the C ABI) against the reference's golden outputs and the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import _support as S
+import sboxgates_b200 as sb
+from sboxgates_b200.rng import Xorshift1024
+
+pytestmark = pytest.mark.gpu
+
+FULL = np.full(4, np.uint64(2**64 - 1), dtype=np.uint64)
+
+
+def _run_gpu(engine, rec_or_case, rng):
+    which, tables, target, mask, inbits = rec_or_case
+    fn = sb.search_5lut if which == 5 else sb.search_7lut
+    return fn(engine, tables, target, mask, inbits, rng)
+
+
+def _replay(engine, path, limit_ns=None):
+    n = 0
+    for rec in S.read_records(path):
+        rng = Xorshift1024.from_state(rec.rng_s, rec.rng_p)
+        res = _run_gpu(engine, (rec.which, rec.tables, rec.target, rec.mask, rec.inbits_list()), rng)
+        assert res.found == rec.found, (path, n)
+        assert res.ret == rec.ret, (path, n, res.ret, rec.ret)
+        assert rng.draws == rec.draws, (path, n)
+        n += 1
+    return n
+
+
+def test_reference_cases(engine):
+    """Synthetic + edge cases answered by the reference's own object code (incl. stale-cache)."""
+    assert _replay(engine, os.path.join(S.GOLDEN, "ref_cases.bin")) >= 60
+
+
+@pytest.mark.parametrize("name", ["run_crypto1_fa_seed1.bin", "run_crypto1_fb_seed1.bin",
+                                  "run_crypto1_fc_seed1.bin", "run_crypto1_fc_seed2.bin",
+                                  "run_des_s1_seed1.bin", "run_des_s1_seed2.bin",
+                                  "run_rijndael_seed1.bin", "run_sodark_seed1.bin"])
+def test_recorded_reference_runs(engine, name):
+    """Every search call of seeded reference runs, including the ones that took the reference
+    minutes: same found / ret[10] / RNG draw count."""
+    path = os.path.join(S.GOLDEN, name)
+    assert os.path.exists(path), "golden fixture missing: run oracle/gen_golden.py"
+    if os.path.getsize(path) == 0:
+        pytest.skip("run made no search calls (fewer than 5 gates)")
+    assert _replay(engine, path) > 0
+
+
+def test_random_vs_oracle(engine):
+    """Seeded random states against the CPU oracle at sizes it finishes in seconds."""
+    sbox = S.rijndael_sbox()
+    rs = np.random.RandomState(42)
+    for i in range(40):
+        n = int(rs.choice([7, 8, 9, 10, 11, 12, 13]))
+        tabs = S.synthetic_state(n, seed=900 + i, num_inputs=min(8, n))
+        fixed = [(int(b), int(rs.randint(0, 2))) for b in rs.choice(8, int(rs.randint(0, 4)),
+                                                                    replace=False)]
+        mask = S.mux_mask(fixed)
+        inb = [b for b, _ in fixed if b < n]
+        tgt = S.sbox_target(sbox, int(rs.randint(0, 8)))
+        for which in (5, 7):
+            seed = rs.bytes(128)
+            o_rng = S.OrcRng.from_seed(seed)
+            g_rng = Xorshift1024(seed)
+            found, ret, st = S.oracle_search(which, tabs, tgt, mask, inb, o_rng)
+            if which == 7 and st.tuples_feasible > 12 and not found:
+                continue  # oracle too slow; covered by properties below
+            res = _run_gpu(engine, (which, tabs, tgt, mask, inb), g_rng)
+            assert (res.found, res.ret) == (found, ret), (i, which, n, fixed)
+            assert g_rng.draws == o_rng.draws
+            if which == 7:
+                assert res.tuples_feasible == st.tuples_feasible
+
+
+def test_filter7_list_matches_oracle(engine):
+    sbox = S.rijndael_sbox()
+    for i, (n, fixed) in enumerate([(12, [(0, 1), (3, 0)]), (14, [(1, 1), (2, 1), (6, 0)]),
+                                    (16, [(5, 0)]), (11, [(0, 0), (1, 0), (2, 0), (3, 0)])]):
+        tabs = S.synthetic_state(n, seed=50 + i)
+        mask = S.mux_mask(fixed)
+        inb = [b for b, _ in fixed]
+        tgt = S.sbox_target(sbox, i)
+        want, _ = S.oracle_filter7(tabs, tgt, mask, inb)
+        engine.load(tabs, tgt, mask, inb)
+        got = engine.filter7_part(0, 1)
+        assert [sb.lut.unpack_tuple7(p) for p in got] == want.tolist()
+
+
+def _verify_result(which, tabs, tgt, mask, res):
+    """The reference's own acceptance test of a result (lut.c:573-576, 617-621)."""
+    r = res.ret
+    if which == 5:
+        t_outer = S.lut_table(r[0], tabs[r[2]], tabs[r[3]], tabs[r[4]])
+        t_inner = S.lut_table(r[1], t_outer, tabs[r[5]], tabs[r[6]])
+    else:
+        t_outer = S.lut_table(r[0], tabs[r[3]], tabs[r[4]], tabs[r[5]])
+        t_mid = S.lut_table(r[1], tabs[r[6]], tabs[r[7]], tabs[r[8]])
+        t_inner = S.lut_table(r[2], t_outer, t_mid, tabs[r[9]])
+    assert not np.any((t_inner ^ tgt) & mask)
+
+
+def test_large_states_properties(engine):
+    """At sizes the oracle cannot reach: planted circuits must be found, results must verify, the
+    answer must not depend on mask compression (an all-ones mask with a masked-equivalent target)
+    or on how the work is split into parts."""
+    rs = np.random.RandomState(77)
+    for n in (40, 64, 96):
+        tabs = S.synthetic_state(n, seed=n)
+        g5 = [int(x) for x in rs.choice(n, 5, replace=False)]
+        t_outer = S.lut_table(0x6A, tabs[g5[0]], tabs[g5[1]], tabs[g5[2]])
+        tgt = S.lut_table(0xC5, t_outer, tabs[g5[3]], tabs[g5[4]])
+        seed = rs.bytes(128)
+        res = sb.search_5lut(engine, tabs, tgt, FULL, [], Xorshift1024(seed))
+        assert res.found
+        _verify_result(5, tabs, tgt, FULL, res)
+        # minimality: the planted combination cannot precede the reported one
+        assert sorted(res.gates) <= sorted(g5)
+        # split into 3 parts -> same key
+        order = sb.shuffled_order(Xorshift1024(seed))
+        engine.load(tabs, tgt, FULL, [])
+        keys = [engine.search5_part(p, 3, order) for p in range(3)]
+        assert min(keys) == res.key
+
+
+def test_planted_7lut_large(engine):
+    rs = np.random.RandomState(78)
+    for n in (24, 32):
+        tabs = S.synthetic_state(n, seed=1000 + n)
+        g7 = [int(x) for x in rs.choice(n, 7, replace=False)]
+        t_outer = S.lut_table(0x96, tabs[g7[0]], tabs[g7[1]], tabs[g7[2]])
+        t_mid = S.lut_table(0xE8, tabs[g7[3]], tabs[g7[4]], tabs[g7[5]])
+        tgt = S.lut_table(0xCA, t_outer, t_mid, tabs[g7[6]])
+        seed = rs.bytes(128)
+        res = sb.search_7lut(engine, tabs, tgt, FULL, [], Xorshift1024(seed))
+        assert res.found
+        _verify_result(7, tabs, tgt, FULL, res)
+        assert sorted(res.gates) <= sorted(g7)
+        # sharded: per-part lists merge to the same list, per-part keys to the same minimum
+        outer, middle = sb.shuffled_orders7(Xorshift1024(seed))
+        engine.load(tabs, tgt, FULL, [])
+        whole = engine.filter7_part(0, 1)
+        parts = [engine.filter7_part(p, 4) for p in range(4)]
+        merged = np.sort(np.concatenate(parts))[:100000]
+        assert merged.tolist() == whole.tolist()
+        engine.set_list7(np.concatenate(parts[::-1]))
+        keys = [engine.decomp7_part(p, 4, outer, middle) for p in range(4)]
+        assert min(keys) == res.key

@@ -1,0 +1,75 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _support as S
+import sboxgates_b200 as sb
+from sboxgates_b200 import native
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(S.ROOT, "include", "sboxgates_b200.h")).read()
+    declared = set(re.findall(r"\b(sbg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    lib = native.load_library()          # raises if the .so or any symbol is missing
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_result_struct_layout_matches_header():
+    # int32 x4, uint8 x4, uint16 x7 + uint16, then four uint64: 72 bytes, no hidden padding.
+    assert C.sizeof(native.SbgResult) == 72
+    assert native.SbgResult.index.offset == 40
+
+
+def test_ordering_rows_match_oracle():
+    assert [sb.ordering_row(7, k) for k in range(70)] == S.order7_rows()
+    assert [sb.ordering_row(5, k) for k in range(10)] == S.order5_rows()
+
+
+def test_host_helpers_match_oracle():
+    lib = S.oracle_lib()
+    rs = np.random.RandomState(5)
+    tabs = S.synthetic_state(16, seed=9)
+    for i in range(200):
+        a, b, c = (tabs[j] for j in rs.choice(16, 3, replace=False))
+        f = int(rs.randint(0, 256))
+        out = np.zeros(4, dtype=np.uint64)
+        lib.orc_lut_ttable(f, S._u64(a)[1], S._u64(b)[1], S._u64(c)[1], out.ctypes.data_as(S.u64p))
+        assert sb.lut_table(f, a, b, c).tolist() == out.tolist()
+        mask = S.mux_mask([(int(rs.randint(0, 8)), int(rs.randint(0, 2)))]) if i % 2 else \
+            np.full(4, np.uint64(2**64 - 1))
+        tgt = S.lut_table(int(rs.randint(0, 256)), a, b, c) if i % 3 else tabs[int(rs.randint(16))]
+        f2, s2 = C.c_uint8(), C.c_uint8()
+        ok2 = lib.orc_solve_inner(S._u64(a)[1], S._u64(b)[1], S._u64(c)[1], S._u64(tgt)[1],
+                                  S._u64(mask)[1], C.byref(f2), C.byref(s2))
+        ok, func, seen = sb.solve_inner(a, b, c, tgt, mask)
+        assert ok == bool(ok2)
+        if ok:
+            assert (func, seen) == (f2.value, s2.value)
+
+
+def test_shuffles_consume_rng_like_reference():
+    seed = open(os.path.join(S.GOLDEN, "seed1.bin"), "rb").read()
+    r = sb.Xorshift1024(seed)
+    order = sb.shuffled_order(r)
+    assert r.draws == 256 and sorted(order) == list(range(256))
+    o, m = sb.shuffled_orders7(r)
+    assert r.draws == 256 + 512 and sorted(o) == list(range(256)) and sorted(m) == list(range(256))
+
+
+def test_engine_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sb.NativeLibraryError):
+        sb.LutEngine(0)
+
+
+def test_missing_library_is_an_error(tmp_path):
+    with pytest.raises(sb.NativeLibraryError):
+        native.load_library(str(tmp_path / "nope.so"))
