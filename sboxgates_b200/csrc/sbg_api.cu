@@ -171,6 +171,7 @@ struct sbg_handle {
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
   float ms[4] = {0, 0, 0, 0};
+  bool sort_pending = false;
   cudaEvent_t ev[8];
   char err[512] = {0};
 };
@@ -222,6 +223,22 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
   return (int)std::min(want, cap);
 }
 
+// Prefixes per ticket batch.  One batch costs one global atomic; batches should hold enough pairs
+// to hide its latency (~64 chunks of 32), leave several batches per resident warp, and never hold
+// more work than a warp's fair share (prefixes are dealt heaviest first, so the tail evens out).
+uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
+  static const char *env = getenv("SBG_BATCH");
+  if (env != nullptr) return std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+  const int K = P + 2;
+  const uint64_t total = h_binom[n][K];
+  const uint64_t avg_pairs = std::max<uint64_t>(1, total / std::max<uint64_t>(1, tickets));
+  const uint64_t qmax = h_binom[n - P][2];
+  uint64_t b = (64 * 32 + avg_pairs - 1) / avg_pairs;
+  b = std::min<uint64_t>(b, std::max<uint64_t>(1, tickets / (warps * 4)));
+  b = std::min<uint64_t>(b, std::max<uint64_t>(1, total / (warps * std::max<uint64_t>(1, qmax))));
+  return std::max<uint64_t>(1, std::min<uint64_t>(16, b));
+}
+
 template <int P>
 int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
   const int n = h->n;
@@ -232,8 +249,10 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
     const size_t smem = sweep_smem<NWV, P>(n);                                                 \
     int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
     if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
+    uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, P);                   \
+    if (max_ctas > 0) bsz = 1;                                                                 \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
-        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP);                       \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);             \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_SWEEP(1) break;
@@ -287,7 +306,10 @@ int fetch_ctl(sbg_handle *h) {
 
 float elapsed(sbg_handle *h, int a, int b) {
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) return 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+    (void)cudaGetLastError();  // do not leave a sticky "last error" behind
+    return 0.f;
+  }
   return ms;
 }
 
@@ -322,10 +344,12 @@ int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
   const size_t total = (size_t)h->h_ctl->hit_count;
   uint32_t keep = 0;
   h->ms[2] = 0.f;
+  h->sort_pending = false;
   if (total > 0) {
     cudaEventRecord(h->ev[2], h->stream);
     if ((rc = sort_hits(h, h->d_hits, h->d_sorted, total)) != SBG_OK) return rc;
     cudaEventRecord(h->ev[3], h->stream);
+    h->sort_pending = true;
     keep = (uint32_t)std::min<size_t>(total, SBG_LIST_CAP);
   }
   *count_out = keep;
@@ -587,10 +611,15 @@ uint64_t sbg_launch_count(const sbg_handle *h) { return h != nullptr ? h->launch
 
 float sbg_last_kernel_ms(const sbg_handle *h, int which) {
   if (h == nullptr || which < 0 || which > 3) return 0.f;
-  if (which == 2) {
+  if (which == 2 && h->sort_pending) {
+    // The sort is timed lazily: its end event has completed by the time any result was fetched.
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) != cudaSuccess) return 0.f;
-    return ms;
+    if (cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ms = 0.f;
+    }
+    const_cast<sbg_handle *>(h)->ms[2] = ms;
+    const_cast<sbg_handle *>(h)->sort_pending = false;
   }
   return h->ms[which];
 }

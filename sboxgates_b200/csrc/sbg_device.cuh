@@ -135,7 +135,8 @@ __device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
 template <int NW, int P>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
-    unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap) {
+    unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
+    int batch) {
   constexpr int K = P + 2;
   constexpr int NC = 1 << P;
   extern __shared__ uint32_t smem[];
@@ -162,22 +163,48 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   const uint32_t inmask = prob->inmask;
   const uint64_t total = c_binom[n - 2][P];
 
-  for (;;) {
-    unsigned long long t = 0;
+  // Work items (prefixes) are handed out in lexicographic order in batches of `batch` consecutive
+  // prefixes: one global atomic per batch, issued one batch ahead so that its latency (and that of
+  // the stop-flag read) overlaps the previous batch's work; inside a batch the prefix and the rank
+  // of its first combination advance incrementally instead of being unranked again.
+  const uint64_t nbatches = (total + (uint64_t)batch - 1) / (uint64_t)batch;
+  unsigned long long swept_local = 0;
+  unsigned long long next_b = 0, next_stop = ~0ull;
+  auto fetch = [&]() {
     if (lane == 0) {
       bool stop = false;
       if (P == 5) stop = volatile_load(&ctl->hit_count) >= list_cap;
-      t = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+      if (P == 3) next_stop = volatile_load(&ctl->stop_ticket);
+      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
     }
-    t = __shfl_sync(kFull, t, 0);
-    if (t == ~0ull) break;
-    const uint64_t gt = t * (uint64_t)nparts + (uint64_t)part;
-    if (gt >= total) break;
-    if (P == 3 && gt > volatile_load(&ctl->stop_ticket)) break;
+  };
+  fetch();
+  bool warp_finished = false;
+  while (!warp_finished) {
+    const unsigned long long b = __shfl_sync(kFull, next_b, 0);
+    const unsigned long long stop_at = __shfl_sync(kFull, next_stop, 0);
+    if (b == ~0ull) break;
+    const uint64_t gb = b * (uint64_t)nparts + (uint64_t)part;
+    if (gb >= nbatches) break;
+    const uint64_t t_first = gb * (uint64_t)batch;
+    if (P == 3 && t_first > stop_at) break;
+    fetch();
+    const uint64_t t_end = min(t_first + (uint64_t)batch, total);
 
     int pre[P];
     uint64_t base_rank;
-    unrank_prefix<P, K>(gt, n, pre, base_rank);
+    unrank_prefix<P, K>(t_first, n, pre, base_rank);
+   for (uint64_t gt = t_first; gt < t_end && !warp_finished; gt++) {
+    if (gt != t_first) {
+      // successor of the prefix among the P-subsets of {0..n-3}; the combinations sharing the
+      // previous prefix were contiguous in rank
+      const int rprev = n - pre[P - 1] - 1;
+      base_rank += (uint64_t)(rprev * (rprev - 1) / 2);
+      int i = P - 1;
+      while (i > 0 && pre[i] + (P - i) >= n - 2) i--;
+      pre[i]++;
+      for (int k2 = i + 1; k2 < P; k2++) pre[k2] = pre[k2 - 1] + 1;
+    }
     bool rejected = false;
 #pragma unroll
     for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
@@ -357,9 +384,11 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
         }
       }
     }
-    if (lane == 0) atomicAdd(&ctl->swept, (unsigned long long)Q);
-    if (P == 3 && warp_done) break;  // every later ticket of this warp has a larger key
+    swept_local += Q;
+    if (P == 3 && warp_done) warp_finished = true;  // every later prefix has a larger key
+   }
   }
+  if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -72,16 +72,13 @@ class DistributedLutSearch:
         return np.concatenate(out)
 
     # -- searches ------------------------------------------------------------------------------
-    def search_5lut(self, tables, target, mask, inbits, rng):
-        order = shuffled_order(rng)
-        self.engine.load(tables, target, mask, inbits)
+    def search5_sharded(self, order):
+        """The current problem's 5-LUT search with a given function order -> raw sbg_result."""
         key = self.engine.search5_part(self.rank, self.world, order)
         key = self._allreduce_min_key(key)
-        return result5_to_ret(self.engine.finish5(key, order), rng)
+        return self.engine.finish5(key, order)
 
-    def search_7lut(self, tables, target, mask, inbits, rng):
-        outer, middle = shuffled_orders7(rng)
-        self.engine.load(tables, target, mask, inbits)
+    def search7_sharded(self, outer, middle):
         local = self.engine.filter7_part(self.rank, self.world)
         merged = self._allgather_lists(local)
         # Every rank installs the same merged list; set_list7 sorts it and keeps the first
@@ -89,4 +86,14 @@ class DistributedLutSearch:
         self.engine.set_list7(merged)
         key = self.engine.decomp7_part(self.rank, self.world, outer, middle)
         key = self._allreduce_min_key(key)
-        return result7_to_ret(self.engine.finish7(key, outer, middle), rng)
+        return self.engine.finish7(key, outer, middle)
+
+    def search_5lut(self, tables, target, mask, inbits, rng):
+        order = shuffled_order(rng)
+        self.engine.load(tables, target, mask, inbits)
+        return result5_to_ret(self.search5_sharded(order), rng)
+
+    def search_7lut(self, tables, target, mask, inbits, rng):
+        outer, middle = shuffled_orders7(rng)
+        self.engine.load(tables, target, mask, inbits)
+        return result7_to_ret(self.search7_sharded(outer, middle), rng)
