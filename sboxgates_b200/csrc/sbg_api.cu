@@ -229,10 +229,11 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
 uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
   static const char *env = getenv("SBG_BATCH");
   if (env != nullptr) return std::max<uint64_t>(1, strtoull(env, nullptr, 10));
-  const int K = P + 2;
-  const uint64_t total = h_binom[n][K];
+  const int K = P == 4 ? 7 : P + 2;
+  // work per ticket in lane-items: (f,g) pairs for the sweeps, (e,f) pairs for the 4-prefix kernel
+  const uint64_t total = P == 4 ? h_binom[n - 1][6] : h_binom[n][K];
   const uint64_t avg_pairs = std::max<uint64_t>(1, total / std::max<uint64_t>(1, tickets));
-  const uint64_t qmax = h_binom[n - P][2];
+  const uint64_t qmax = h_binom[n - P - (P == 4 ? 1 : 0)][2];
   uint64_t b = (64 * 32 + avg_pairs - 1) / avg_pairs;
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, tickets / (warps * 4)));
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, total / (warps * std::max<uint64_t>(1, qmax))));
@@ -264,6 +265,49 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
   h->launches++;
   SBG_CUDA(h, cudaGetLastError());
   return SBG_OK;
+}
+
+template <int NW>
+size_t filter_pm_smem(int n, int m) {
+  const int npad = (n + 3) & ~3;
+  const int ngw = (((n + 31) >> 5) + 1) & ~1;
+  return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3) + kWarpsPerCta * 16 * NW);
+}
+
+// Position-major phase 1 (k_filter7_pm): work items are 4-gate prefixes.
+int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_ctas) {
+  const int n = h->n;
+  const int m = popcount256(h->mask);
+  const uint64_t tickets = (h_binom[n - 3][4] + nparts - 1) / nparts;
+  const unsigned long long cap = h->hits_cap;
+#define SBG_LAUNCH_PM(NWV)                                                                     \
+  {                                                                                            \
+    const size_t smem = filter_pm_smem<NWV>(n, m);                                             \
+    int grid = grid_for(h, k_filter7_pm<NWV>, smem, tickets);                                  \
+    if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
+    uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, 4);                   \
+    if (max_ctas > 0) bsz = 1;                                                                 \
+    k_filter7_pm<NWV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, cap, \
+        part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);                             \
+  }
+  switch (h->nw) {
+    case 1: SBG_LAUNCH_PM(1) break;
+    case 2: SBG_LAUNCH_PM(2) break;
+    case 4: SBG_LAUNCH_PM(4) break;
+    default: SBG_LAUNCH_PM(8) break;
+  }
+#undef SBG_LAUNCH_PM
+  h->launches++;
+  SBG_CUDA(h, cudaGetLastError());
+  return SBG_OK;
+}
+
+// Which phase-1 kernel: the position-major one unless SBG_FILTER=sweep asks for the bitmap sweep.
+bool use_position_major(const sbg_handle *h) {
+  static const char *env = getenv("SBG_FILTER");
+  if (env != nullptr) return strcmp(env, "sweep") != 0;
+  (void)h;
+  return true;
 }
 
 int launch_decomp7(sbg_handle *h, int part, int nparts) {
@@ -328,7 +372,11 @@ int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
   for (int attempt = 0; attempt < 2; attempt++) {
     if ((rc = reset_ctl(h)) != SBG_OK) return rc;
     cudaEventRecord(h->ev[0], h->stream);
-    if ((rc = launch_sweep<5>(h, part, nparts, max_ctas)) != SBG_OK) return rc;
+    if (use_position_major(h)) {
+      if ((rc = launch_filter7_pm(h, part, nparts, max_ctas)) != SBG_OK) return rc;
+    } else if ((rc = launch_sweep<5>(h, part, nparts, max_ctas)) != SBG_OK) {
+      return rc;
+    }
     cudaEventRecord(h->ev[1], h->stream);
     if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
     h->ms[1] = elapsed(h, 0, 1);
@@ -682,6 +730,24 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
     if (inbits[k] >= 0 && inbits[k] < 8) inmask |= 1u << inbits[k];
   }
   p->inmask = inmask;
+  p->m = m;
+  // position-major rows (see DevProblem::xr): bit g of row pos = gate g at that position,
+  // rows of target-0 positions complemented
+  for (int g = 0; g < n; g++) {
+    for (int w = 0; w < 8; w++) {
+      uint32_t bits = p->tabs[w][g];
+      while (bits != 0) {
+        const int b = __builtin_ctz(bits);
+        bits &= bits - 1;
+        p->xr[w * 32 + b][g >> 5] |= 1u << (g & 31);
+      }
+    }
+  }
+  for (int pos = 0; pos < m; pos++) {
+    if (!((p->T[pos >> 5] >> (pos & 31)) & 1u)) {
+      for (int w = 0; w < 16; w++) p->xr[pos][w] = ~p->xr[pos][w];
+    }
+  }
   SBG_CUDA(h, cudaMemcpyAsync(h->d_slots + slot, p, sizeof(DevProblem), cudaMemcpyHostToDevice,
       h->stream));
   return SBG_OK;

@@ -34,7 +34,12 @@ struct DevProblem {
   int32_t n;                       // number of gates
   int32_t nw;                      // words in use: 1, 2, 4 or 8
   uint32_t inmask;                 // bit g set: gate g (< 8) is excluded (lut.c:177-185)
-  int32_t pad;
+  int32_t m;                       // popcount(mask) = number of (compressed) positions
+  // Position-major copy: row p (compressed position) holds one bit per gate, bit g = value of
+  // gate g at position p, the whole row complemented where the target is 0.  So "gate g takes
+  // the target's value on every position of a set S" <=> bit g of AND_{p in S} xr[p], and "gate g
+  // takes the opposite value on all of S" <=> bit g of ~OR_{p in S} xr[p].
+  uint32_t xr[256][16];
 };
 
 struct DevCtl {
@@ -205,13 +210,14 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       pre[i]++;
       for (int k2 = i + 1; k2 < P; k2++) pre[k2] = pre[k2 - 1] + 1;
     }
+    const int last = pre[P - 1];
+    const int r = n - last - 1;
+    const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
+    swept_local += Q;
     bool rejected = false;
 #pragma unroll
     for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
     if (rejected) continue;
-    const int last = pre[P - 1];
-    const int r = n - last - 1;
-    const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
 
     // Prefix cells: lane = cell index, first prefix gate = most significant bit (lut.c:46-49).
     uint32_t mixed_ballot;
@@ -384,9 +390,231 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
         }
       }
     }
-    swept_local += Q;
     if (P == 3 && warp_done) warp_finished = true;  // every later prefix has a larger key
    }
+  }
+  if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Phase 1 of search_7lut, position-major form (lut.c:294-327).
+//
+// One warp per 4-gate prefix (a,b,c,d); lanes take the (e,f) pairs; the last gate g is not
+// enumerated at all: each lane computes the SET of feasible g as a bit vector over gates.
+// For a mixed cell C of the prefix and each of the four (e,f)-parts of it, let A / B be the part's
+// positions with target 1 / 0.  If both are non-empty, g is admissible for that part iff it is
+// constant on A, constant on B and different between them, i.e. iff bit g of
+//     AND_{p in part} xr[p]   |   ~OR_{p in part} xr[p]
+// is set (xr = position-major rows, complemented where the target is 0).  Intersecting over parts and
+// cells gives exactly the g for which check_n_lut_possible(7, ...) holds (lut.c:34-66); the vector
+// usually empties after the first cell.  Cost per lane: ~30 instructions per visited position for
+// up to 64 candidate g, against ~100 per (pair, cell) in k_sweep.
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
+    int nparts, unsigned long long list_cap, int batch) {
+  constexpr int P = 4, K = 7, NC = 16, W = 2;
+  extern __shared__ uint32_t smem[];
+  const int n = prob->n;
+  const int m = prob->m;
+  const int npad = (n + 3) & ~3;
+  const int ngw = (((n + 31) >> 5) + 1) & ~1;      // gate words per row, even
+  uint32_t *s_tabs = smem;                         // NW * npad   gate-major
+  uint32_t *s_xr = smem + NW * npad;               // m * ngw     position-major
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint32_t *cells = s_xr + ((m * ngw + 3) & ~3) + warp * (NC * NW);
+
+  for (int i = threadIdx.x; i < m * ngw; i += blockDim.x) {
+    s_xr[i] = prob->xr[i / ngw][i % ngw];
+  }
+  stage_tables(s_tabs, prob, NW, npad);
+
+  uint32_t T[NW], M[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    T[w] = prob->T[w];
+    M[w] = prob->M[w];
+  }
+  const uint32_t inmask = prob->inmask;
+  const uint64_t total = c_binom[n - 3][P];
+  const uint64_t nbatches = (total + (uint64_t)batch - 1) / (uint64_t)batch;
+  unsigned long long swept_local = 0;
+  unsigned long long next_b = 0;
+  auto fetch = [&]() {
+    if (lane == 0) {
+      const bool stop = volatile_load(&ctl->hit_count) >= list_cap;
+      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+    }
+  };
+  fetch();
+  for (;;) {
+    const unsigned long long b = __shfl_sync(kFull, next_b, 0);
+    if (b == ~0ull) break;
+    const uint64_t gb = b * (uint64_t)nparts + (uint64_t)part;
+    if (gb >= nbatches) break;
+    const uint64_t t_first = gb * (uint64_t)batch;
+    fetch();
+    const uint64_t t_end = min(t_first + (uint64_t)batch, total);
+    int pre[P];
+    uint64_t unused_rank;
+    unrank_prefix<P, K>(t_first, n, pre, unused_rank);
+    for (uint64_t gt = t_first; gt < t_end; gt++) {
+      if (gt != t_first) {
+        int i = P - 1;
+        while (i > 0 && pre[i] + (P - i) >= n - 3) i--;
+        pre[i]++;
+        for (int k2 = i + 1; k2 < P; k2++) pre[k2] = pre[k2 - 1] + 1;
+      }
+      const int last = pre[P - 1];
+      const int r = n - last - 2;                   // candidates for e,f: last+1 .. n-2
+      const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
+      swept_local += c_binom[n - last - 1][3];      // 7-combinations sharing this prefix
+      bool rejected = false;
+#pragma unroll
+      for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
+      if (rejected) continue;
+
+      // mixed cells of the prefix (lane < 16 = cell, first gate most significant)
+      uint32_t mixed_ballot;
+      {
+        uint32_t c[NW];
+        uint32_t ones = 0, zeros = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+          uint32_t tt = M[w];
+#pragma unroll
+          for (int i = 0; i < P; i++) {
+            const uint32_t tv = s_tabs[w * npad + pre[i]];
+            tt &= ((lane >> (P - 1 - i)) & 1) ? tv : ~tv;
+          }
+          c[w] = tt;
+          ones |= tt & T[w];
+          zeros |= tt & ~T[w];
+        }
+        const bool mixed = lane < NC && ones != 0 && zeros != 0;
+        mixed_ballot = __ballot_sync(kFull, mixed);
+        __syncwarp();
+        if (mixed) {
+          const int slot = __popc(mixed_ballot & lanemask_lt());
+#pragma unroll
+          for (int w = 0; w < NW; w++) cells[slot * NW + w] = c[w];
+        }
+        __syncwarp();
+      }
+      const int mc = __popc(mixed_ballot);
+
+      unsigned long long emitted = 0;
+      bool prefix_done = false;
+      for (uint32_t q0 = 0; q0 < Q && !prefix_done; q0 += 32) {
+        const uint32_t q = q0 + lane;
+        bool lane_ok = q < Q;
+        int pi, pj;
+        unrank_pair(lane_ok ? q : 0u, r, pi, pj);
+        const int ge = last + 1 + pi;
+        const int gf = last + 1 + pj;
+        if ((ge < 8 && ((inmask >> ge) & 1u)) || (gf < 8 && ((inmask >> gf) & 1u))) lane_ok = false;
+        uint32_t te[NW], tf[NW];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+          te[w] = s_tabs[w * npad + ge];
+          tf[w] = s_tabs[w * npad + gf];
+        }
+        // windows of 64 candidate gates g; the first window that can hold a g > last + 2
+        for (int wb = ((last + 3) >> 5) & ~(W - 1); wb < ngw; wb += W) {
+          uint32_t V[W];
+#pragma unroll
+          for (int j = 0; j < W; j++) {
+            const int g0 = (wb + j) * 32;           // gates g0 .. g0+31: keep gf < g < n
+            uint32_t v = 0xffffffffu;
+            if (n - g0 < 32) v = (n - g0 <= 0) ? 0u : (0xffffffffu >> (32 - (n - g0)));
+            if (gf + 1 - g0 >= 32) v = 0u;
+            else if (gf + 1 - g0 > 0) v &= 0xffffffffu << (gf + 1 - g0);
+            if (g0 == 0) v &= ~inmask;
+            V[j] = lane_ok ? v : 0u;
+          }
+          bool alive = (V[0] | V[1]) != 0;
+          for (int cj = 0; cj < mc; cj++) {
+            if (!__any_sync(kFull, alive)) break;
+            uint32_t a_and[4][W], a_or[4][W];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+#pragma unroll
+              for (int j = 0; j < W; j++) {
+                a_and[k][j] = 0xffffffffu;
+                a_or[k][j] = 0u;
+              }
+            }
+            uint32_t has1 = 0, has0 = 0;
+#pragma unroll
+            for (int w = 0; w < NW; w++) {
+              uint32_t bits = cells[cj * NW + w];
+              while (bits != 0) {                     // warp-uniform loop over the cell's positions
+                const int j = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int p = w * 32 + j;
+                const uint32_t tp = (T[w] >> j) & 1u;
+                const uint32_t pk = (((te[w] >> j) & 1u) << 1) | ((tf[w] >> j) & 1u);
+                const uint2 x = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
+                if (tp) has1 |= 1u << pk; else has0 |= 1u << pk;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const uint32_t mk = (pk == (uint32_t)k) ? 0xffffffffu : 0u;
+                  a_and[k][0] &= x.x | ~mk;
+                  a_and[k][1] &= x.y | ~mk;
+                  a_or[k][0] |= x.x & mk;
+                  a_or[k][1] |= x.y & mk;
+                }
+              }
+            }
+            const uint32_t both = has1 & has0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              if ((both >> k) & 1u) {
+                V[0] &= a_and[k][0] | ~a_or[k][0];
+                V[1] &= a_and[k][1] | ~a_or[k][1];
+              }
+            }
+            alive = (V[0] | V[1]) != 0;
+          }
+          // emit every surviving g of every lane
+          const int cnt = __popc(V[0]) + __popc(V[1]);
+          int incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += up;
+          }
+          const int warp_total = __shfl_sync(kFull, incl, 31);
+          if (warp_total == 0) continue;
+          unsigned long long base_slot = 0;
+          if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)warp_total);
+          base_slot = __shfl_sync(kFull, base_slot, 0) + (unsigned long long)(incl - cnt);
+          uint64_t head = 0;
+#pragma unroll
+          for (int i = 0; i < P; i++) head = (head << 9) | (uint64_t)pre[i];
+          head = (head << 27) | ((uint64_t)ge << 18) | ((uint64_t)gf << 9);
+#pragma unroll
+          for (int j = 0; j < W; j++) {
+            uint32_t v = V[j];
+            while (v != 0) {
+              const int gbit = __ffs(v) - 1;
+              v &= v - 1;
+              if (base_slot < hits_cap) {
+                hits[base_slot] = head | (uint64_t)((wb + j) * 32 + gbit);
+              } else {
+                atomicExch(&ctl->overflow, 1u);
+              }
+              base_slot++;
+            }
+          }
+          emitted += (unsigned long long)warp_total;
+        }
+        // One prefix never needs to contribute more than the list cap (lut.c:316-318); checked only
+        // between chunks, when every pair up to here has all its g emitted.
+        if (emitted >= list_cap) prefix_done = true;
+      }
+    }
   }
   if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
 }
