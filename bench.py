@@ -137,12 +137,12 @@ def units_of(n, r5, r7):
     c = int(r5.tuples_feasible) * C_PER_5
     if r5.found:
         c = max(0, int(r5.tuples_feasible) - 1) * C_PER_5 + r5.ordering * 256 + r5.pos_outer + 1
-    t += int(r7.tuples_swept) if r7.tuples_swept else math.comb(n, 7)
+    t7 = int(r7.tuples_swept)      # this rank's share; summed over ranks by the caller
     if r7.found:
         c += int(r7.index) * C_PER_7 + r7.ordering * 65536 + r7.pos_outer * 256 + r7.pos_middle + 1
     else:
         c += int(r7.tuples_feasible) * C_PER_7
-    return t, c
+    return t, t7, c
 
 
 # ------------------------------------------------------------------------------------------------
@@ -347,10 +347,10 @@ def main():
                 k5 = eng.kernel_ms(0)
                 r7 = drv.search7_sharded(st["outer"], st["middle"])
             if acc is not None:
-                t, c = units_of(n, r5, r7)
-                acc["T"] += t
+                t5, t7, c = units_of(n, r5, r7)
+                acc["T"] += t5
                 acc["C"] += c
-                acc["T7"] += math.comb(n, 7) if not r7.tuples_swept else int(r7.tuples_swept) * world
+                acc["T7"] += t7
                 acc["ms5"] += k5
                 acc["ms_filter"] += eng.kernel_ms(1)
                 acc["ms_sort"] += eng.kernel_ms(2)
@@ -394,6 +394,14 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        if world > 1:   # phase-1 tuples are swept by different ranks: sum the shares
+            t = torch.tensor([acc["T7"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            acc["T7"] = int(t.item())
+            t = torch.tensor([acc["ms_filter"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            acc["ms_filter"] = float(t.item())
+        acc["T"] += acc["T7"]
         acc["launches"] = eng.launches - launches0
         return ms, acc, clocks
 
@@ -409,13 +417,13 @@ def main():
         except OSError:
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: the 7-LUT phase-1 sweep (k_sweep<NW,5>), one launch per state per step
+        # dominant kernel: the 7-LUT phase-1 sweep, one launch per state per step
         filt_s = acc_res["ms_filter"] * 1e-3
         achieved = acc_res["T7"] * BYTES_T7 / max(filt_s, 1e-12) / 1e9
         dram_per_launch = None
         try:
             dram_per_launch = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[
-                "k_sweep_filter7_bytes_per_launch"]
+                "filter7_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
         line = {
@@ -435,7 +443,7 @@ def main():
                     "note": "host tables -> sbg_load_problem -> sbg_search5/7 -> result structs"},
             "gpu_launches": acc_res["launches"],
             "roofline": {
-                "bound": "hbm", "kernel": "k_sweep<NW,5> (search_7lut phase 1)",
+                "bound": "hbm", "kernel": "k_filter7_pm<NW> (search_7lut phase 1)",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "traffic": dram_per_launch,

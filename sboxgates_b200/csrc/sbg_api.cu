@@ -132,10 +132,19 @@ struct sbg_handle {
   DevProblem *d_prob = nullptr;  // the problem in use (points into d_slots)
   DevProblem *d_slots = nullptr; // kSlots device-resident problems
   DevProblem *h_prob = nullptr;  // pinned staging copy
-  DevCtl *d_ctl = nullptr;
-  DevCtl *h_ctl = nullptr;       // pinned
-  DevParams7 *d_par7 = nullptr;
-  DevParams7 *h_par7 = nullptr;  // pinned
+  // per-call block: control words + 7-LUT parameters, contiguous so one copy uploads both
+  struct DevCall {
+    DevCtl ctl;
+    DevParams7 par;
+  };
+  DevCall *d_call = nullptr;
+  DevCall *h_call = nullptr;     // pinned
+  DevCtl *d_ctl = nullptr;       // = &d_call->ctl
+  DevCtl *h_ctl = nullptr;       // = &h_call->ctl
+  DevParams7 *d_par7 = nullptr;  // = &d_call->par
+  DevParams7 *h_par7 = nullptr;  // = &h_call->par
+  DevCtl *h_ctl_out = nullptr;   // pinned: control words read back
+  uint64_t *h_head = nullptr;    // pinned: first kHeadEntries of the sorted list, read back with them
   uint8_t *d_pos5 = nullptr;
   uint8_t *h_pos5 = nullptr;     // pinned
 
@@ -156,6 +165,7 @@ struct sbg_handle {
     uint64_t mask[4];
     int n = 0;
     int nw = 0;
+    uint32_t inmask = 0;
     bool ready = false;
   };
   HostProblem *slots = nullptr;  // kSlots entries
@@ -179,6 +189,7 @@ struct sbg_handle {
 namespace {
 
 constexpr int kSlots = SBG_PROBLEM_SLOTS;
+constexpr size_t kHeadEntries = 1024;  // list entries read back together with the control words
 
 int fail(sbg_handle *h, int code, const char *fmt, ...) {
   if (h != nullptr) {
@@ -310,15 +321,19 @@ bool use_position_major(const sbg_handle *h) {
   return true;
 }
 
-int launch_decomp7(sbg_handle *h, int part, int nparts) {
+// count_on_device: the list length is ctl->list_count (written by k_sort_small); the grid is then
+// sized for the longest list that kernel sorts, surplus CTAs return before staging anything.
+int launch_decomp7(sbg_handle *h, int part, int nparts, bool count_on_device = false) {
   const int n = h->n;
-  const uint64_t items = (h->list_count + nparts - 1) / nparts;
+  const uint64_t items = count_on_device ? (uint64_t)kSmallSort
+                                         : (h->list_count + nparts - 1) / nparts;
+  const unsigned int count_arg = count_on_device ? 0xffffffffu : h->list_count;
 #define SBG_LAUNCH_DECOMP(NWV)                                                                 \
   {                                                                                            \
     const size_t smem = decomp_smem<NWV>(n);                                                   \
     const int grid = grid_for(h, k_decomp7<NWV>, smem, items);                                 \
     k_decomp7<NWV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_par7,        \
-        h->d_list, h->list_count, part, nparts);                                               \
+        h->d_list, count_arg, part, nparts);                                                   \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_DECOMP(1) break;
@@ -342,9 +357,10 @@ int reset_ctl(sbg_handle *h) {
 }
 
 int fetch_ctl(sbg_handle *h) {
-  SBG_CUDA(h, cudaMemcpyAsync(h->h_ctl, h->d_ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost,
+  SBG_CUDA(h, cudaMemcpyAsync(h->h_ctl_out, h->d_ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost,
       h->stream));
   SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  *h->h_ctl = *h->h_ctl_out;
   return SBG_OK;
 }
 
@@ -609,10 +625,14 @@ int sbg_create(sbg_handle **out, int device) {
   h->d_prob = h->d_slots;
   h->slots = new sbg_handle::HostProblem[kSlots];
   SBG_CUDA(h, cudaMallocHost(&h->h_prob, sizeof(DevProblem)));
-  SBG_CUDA(h, cudaMalloc(&h->d_ctl, sizeof(DevCtl)));
-  SBG_CUDA(h, cudaMallocHost(&h->h_ctl, sizeof(DevCtl)));
-  SBG_CUDA(h, cudaMalloc(&h->d_par7, sizeof(DevParams7)));
-  SBG_CUDA(h, cudaMallocHost(&h->h_par7, sizeof(DevParams7)));
+  SBG_CUDA(h, cudaMalloc(&h->d_call, sizeof(sbg_handle::DevCall)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_call, sizeof(sbg_handle::DevCall)));
+  h->d_ctl = &h->d_call->ctl;
+  h->h_ctl = &h->h_call->ctl;
+  h->d_par7 = &h->d_call->par;
+  h->h_par7 = &h->h_call->par;
+  SBG_CUDA(h, cudaMallocHost(&h->h_ctl_out, sizeof(DevCtl)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_head, kHeadEntries * sizeof(uint64_t)));
   SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
   SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
   const char *cap_env = getenv("SBG_HITS_CAP");
@@ -635,8 +655,8 @@ void sbg_destroy(sbg_handle *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_slots); cudaFreeHost(h->h_prob);
-    cudaFree(h->d_ctl); cudaFreeHost(h->h_ctl);
-    cudaFree(h->d_par7); cudaFreeHost(h->h_par7);
+    cudaFree(h->d_call); cudaFreeHost(h->h_call);
+    cudaFreeHost(h->h_ctl_out); cudaFreeHost(h->h_head);
     cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
     cudaFree(h->d_hits); cudaFree(h->d_sorted); cudaFree(h->d_cub);
     cudaFreeHost(h->h_list);
@@ -698,9 +718,20 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
   }
   if (n < 1 || n > SBG_MAX_GATES) return fail(h, SBG_ERR_ARG, "n = %d out of range", n);
   SBG_CUDA(h, cudaSetDevice(h->device));
+  sbg_handle::HostProblem &hp = h->slots[slot];
+  uint32_t inmask = 0;
+  for (int k = 0; k < 8 && inbits[k] != -1; k++) {
+    if (inbits[k] >= 0 && inbits[k] < 8) inmask |= 1u << inbits[k];
+  }
+  // lut_search calls search_5lut and then search_7lut on the same state (lut.c:553,593): the second
+  // upload is skipped when nothing changed
+  if (hp.ready && hp.n == n && hp.inmask == inmask && memcmp(hp.target, target, 32) == 0
+      && memcmp(hp.mask, mask, 32) == 0 && memcmp(hp.tables, tables, (size_t)n * 32) == 0) {
+    return SBG_OK;
+  }
   // The pinned staging block may still be in flight from the previous upload.
   SBG_CUDA(h, cudaStreamSynchronize(h->stream));
-  sbg_handle::HostProblem &hp = h->slots[slot];
+  hp.inmask = inmask;
   memcpy(hp.tables, tables, (size_t)n * 32);
   memcpy(hp.target, target, 32);
   memcpy(hp.mask, mask, 32);
@@ -724,10 +755,6 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
   for (int g = 0; g < n; g++) {
     compress_table(tables + 4 * g, mask, tmp);
     for (int w = 0; w < 8; w++) p->tabs[w][g] = tmp[w] & cm[w];
-  }
-  uint32_t inmask = 0;
-  for (int k = 0; k < 8 && inbits[k] != -1; k++) {
-    if (inbits[k] >= 0 && inbits[k] < 8) inmask |= 1u << inbits[k];
   }
   p->inmask = inmask;
   p->m = m;
@@ -861,8 +888,8 @@ int sbg_decomp7_part(sbg_handle *h, int part, int nparts, const uint8_t *outer_o
   return run_decomp7(h, part, nparts, outer_order, middle_order, key);
 }
 
-int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
-    const uint8_t *middle_order, sbg_result *res) {
+static int finish7_impl(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
+    const uint8_t *middle_order, sbg_result *res, const uint64_t *head, size_t head_len) {
   if (h == nullptr || res == nullptr || outer_order == nullptr || middle_order == nullptr) {
     return SBG_ERR_ARG;
   }
@@ -879,9 +906,14 @@ int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
   SBG_CUDA(h, cudaSetDevice(h->device));
   uint64_t pair[2] = {0, 0};
   const size_t first = idx > 0 ? idx - 1 : 0;
-  SBG_CUDA(h, cudaMemcpyAsync(pair, h->d_list + first, (idx > 0 ? 2 : 1) * sizeof(uint64_t),
-      cudaMemcpyDeviceToHost, h->stream));
-  SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (head != nullptr && idx < head_len) {   // already on the host
+    pair[0] = head[first];
+    pair[1] = head[idx];
+  } else {
+    SBG_CUDA(h, cudaMemcpyAsync(pair, h->d_list + first, (idx > 0 ? 2 : 1) * sizeof(uint64_t),
+        cudaMemcpyDeviceToHost, h->stream));
+    SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   const uint64_t cur = idx > 0 ? pair[1] : pair[0];
   uint16_t t[7];
   for (int i = 0; i < 7; i++) t[i] = (uint16_t)((cur >> (9 * (6 - i))) & 0x1ff);
@@ -916,16 +948,79 @@ int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
   return SBG_OK;
 }
 
+int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
+    const uint8_t *middle_order, sbg_result *res) {
+  return finish7_impl(h, key, outer_order, middle_order, res, nullptr, 0);
+}
+
+// Whole search_7lut on one device.  Fast path: upload (control words + parameters, one copy) ->
+// phase 1 -> on-device sort of a short hit list -> phase 2 -> one read-back, i.e. a single host
+// synchronisation per call.  Long lists (more than kSmallSort hits) take the step-by-step path
+// with CUB's radix sort.
 int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle_order,
     sbg_result *res) {
   if (h == nullptr || res == nullptr) return SBG_ERR_ARG;
-  int count = 0;
-  int rc = sbg_filter7_part(h, 0, 1, nullptr, &count);
-  if (rc != SBG_OK) return rc;
-  h->list_ready = true;  // the device-resident sorted list of the only part is the list
+  if (!h->problem_ready) return fail(h, SBG_ERR_STATE, "no problem loaded");
+  if (h->n < 7) return fail(h, SBG_ERR_ARG, "search_7lut needs n >= 7 (lut.c:259)");
+  if (!valid_order(outer_order) || !valid_order(middle_order)) {
+    return fail(h, SBG_ERR_ARG, "function order is not a permutation");
+  }
+  SBG_CUDA(h, cudaSetDevice(h->device));
+  int rc;
+  build_params7(h, outer_order, middle_order);
+  DevCtl *c = h->h_ctl;
+  memset(c, 0, sizeof(*c));
+  c->best = ~0ull;
+  c->stop_ticket = ~0ull;
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_call, h->h_call, sizeof(sbg_handle::DevCall),
+      cudaMemcpyHostToDevice, h->stream));
+  cudaEventRecord(h->ev[0], h->stream);
+  if (use_position_major(h)) {
+    if ((rc = launch_filter7_pm(h, 0, 1, 0)) != SBG_OK) return rc;
+  } else if ((rc = launch_sweep<5>(h, 0, 1, 0)) != SBG_OK) {
+    return rc;
+  }
+  cudaEventRecord(h->ev[1], h->stream);
+  k_sort_small<<<1, 1024, 0, h->stream>>>(h->d_hits, h->d_sorted, h->d_ctl,
+      (unsigned int)SBG_LIST_CAP);
+  h->launches++;
+  cudaEventRecord(h->ev[4], h->stream);
+  h->d_list = h->d_sorted;
+  if ((rc = launch_decomp7(h, 0, 1, true)) != SBG_OK) return rc;
+  cudaEventRecord(h->ev[5], h->stream);
+  SBG_CUDA(h, cudaMemcpyAsync(h->h_head, h->d_sorted, kHeadEntries * sizeof(uint64_t),
+      cudaMemcpyDeviceToHost, h->stream));
+  if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+  h->ms[1] = elapsed(h, 0, 1);
+  h->ms[2] = elapsed(h, 1, 4);
+  h->ms[3] = elapsed(h, 4, 5);
+  h->sort_pending = false;
+  h->swept = h->h_ctl->swept;
+
+  if (h->h_ctl->overflow == 0 && h->h_ctl->sorted_ok != 0) {
+    h->list_count = h->h_ctl->list_count;
+    h->list_ready = true;
+    return finish7_impl(h, h->h_ctl->best, outer_order, middle_order, res, h->h_head,
+        std::min<size_t>(kHeadEntries, h->list_count));
+  }
+  uint32_t keep = 0;
+  if (h->h_ctl->overflow != 0) {
+    // hit buffer overflowed: redo phase 1 with the bounded-parallelism retry
+    if ((rc = run_filter7(h, 0, 1, &keep)) != SBG_OK) return rc;
+  } else {
+    // long list: phase 1 is done, sort its hits with CUB
+    const size_t total = (size_t)h->h_ctl->hit_count;
+    cudaEventRecord(h->ev[2], h->stream);
+    if ((rc = sort_hits(h, h->d_hits, h->d_sorted, total)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[3], h->stream);
+    h->sort_pending = true;
+    keep = (uint32_t)std::min<size_t>(total, SBG_LIST_CAP);
+  }
+  h->d_list = h->d_sorted;
+  h->list_count = keep;
+  h->list_ready = true;
   uint64_t key = SBG_KEY_NONE;
-  rc = sbg_decomp7_part(h, 0, 1, outer_order, middle_order, &key);
-  if (rc != SBG_OK) return rc;
+  if ((rc = run_decomp7(h, 0, 1, outer_order, middle_order, &key)) != SBG_OK) return rc;
   return sbg_finish7(h, key, outer_order, middle_order, res);
 }
 

@@ -49,7 +49,10 @@ struct DevCtl {
   unsigned long long hit_count;    // filter7: feasible tuples appended
   unsigned long long swept;        // tuples put through the feasibility test
   unsigned long long feasible;     // search5: feasible tuples met
+  unsigned long long ticket2;      // decomp7: next list entry (phase 2 runs after phase 1 without a reset)
   unsigned int overflow;           // filter7: hit buffer too small
+  unsigned int list_count;         // written by k_sort_small: entries of the sorted list
+  unsigned int sorted_ok;          // 1 if k_sort_small produced the sorted list on the device
   unsigned int pad;
 };
 
@@ -620,6 +623,52 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ordering the phase-1 hits (lut.c:329-349 concatenates per-rank lists in rank order, which at
+// size 1 is lexicographic order).  Short lists -- the common case -- are sorted by one CTA with a
+// bitonic network in shared memory, the count being read on the device so that phase 2 can be
+// launched without a host round trip; longer lists go through CUB on the host's initiative.
+constexpr int kSmallSort = 4096;
+
+__global__ void __launch_bounds__(1024) k_sort_small(const uint64_t *__restrict__ hits,
+    uint64_t *__restrict__ sorted, DevCtl *__restrict__ ctl, unsigned int list_cap) {
+  __shared__ uint64_t keys[kSmallSort];
+  const unsigned long long total = ctl->hit_count;
+  if (total > (unsigned long long)kSmallSort || ctl->overflow != 0) {
+    if (threadIdx.x == 0) {
+      ctl->sorted_ok = 0;
+      ctl->list_count = 0;
+    }
+    return;
+  }
+  const unsigned int cnt = (unsigned int)total;
+  unsigned int npow = 1;
+  while (npow < cnt) npow <<= 1;
+  for (unsigned int i = threadIdx.x; i < npow; i += blockDim.x) keys[i] = i < cnt ? hits[i] : ~0ull;
+  __syncthreads();
+  for (unsigned int k = 2; k <= npow; k <<= 1) {
+    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+      for (unsigned int i = threadIdx.x; i < npow; i += blockDim.x) {
+        const unsigned int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sorted[i] = keys[i];
+  if (threadIdx.x == 0) {
+    ctl->list_count = cnt < list_cap ? cnt : list_cap;
+    ctl->sorted_ok = 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Phase 2 of search_7lut (lut.c:416-484): one warp per feasible 7-tuple.
 
 __device__ __forceinline__ uint32_t compress16(uint32_t r16, int b, int z) {
@@ -687,6 +736,15 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   __shared__ uint8_t s_pos[256];
   __shared__ uint32_t s_H[kWarpsPerCta][24];
 
+  if (count == 0xffffffffu) {  // list produced on the device by k_sort_small
+    if (ctl->sorted_ok == 0) return;
+    count = ctl->list_count;
+  }
+  // this part's share is ceil((count - part) / nparts) entries; surplus CTAs leave at once
+  const unsigned int share = count > (unsigned int)part
+      ? (count - (unsigned int)part + (unsigned int)nparts - 1) / (unsigned int)nparts : 0u;
+  if (blockIdx.x * kWarpsPerCta >= share) return;
+
   const int n = prob->n;
   const int npad = (n + 3) & ~3;
   uint32_t *s_tabs = smem;
@@ -710,7 +768,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
 
   for (;;) {
     unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(&ctl->ticket, 1ull);
+    if (lane == 0) t = atomicAdd(&ctl->ticket2, 1ull);
     t = __shfl_sync(kFull, t, 0);
     const uint64_t idx = t * (uint64_t)nparts + (uint64_t)part;
     if (idx >= count) break;
