@@ -115,7 +115,9 @@ int sbg_finish5(sbg_handle *h, uint64_t key, const uint8_t *func_order, sbg_resu
 /* 7-LUT phase 1: this part's share of C(n,7).  Writes this part's feasible combinations, sorted,
    at most SBG_LIST_CAP of them, as packed 63-bit words (9 bits per gate, first gate in the most
    significant position, so integer order = lexicographic order) to `list` (host memory, room for
-   SBG_LIST_CAP entries) and their number to *count. */
+   SBG_LIST_CAP entries) and their number to *count.  `list` may be NULL (no copy).  With
+   nparts == 1 the device-resident result is installed as the list, so sbg_decomp7_part() may follow
+   directly. */
 int sbg_filter7_part(sbg_handle *h, int part, int nparts, uint64_t *list, int *count);
 /* Installs the merged hit list (any order, duplicates not allowed; it is sorted and truncated to
    SBG_LIST_CAP here, which reproduces lut.c:316-318 for size == 1). */

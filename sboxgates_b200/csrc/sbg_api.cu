@@ -851,9 +851,11 @@ int sbg_filter7_part(sbg_handle *h, int part, int nparts, uint64_t *list, int *c
         cudaMemcpyDeviceToHost, h->stream));
     SBG_CUDA(h, cudaStreamSynchronize(h->stream));
   }
-  // A single part's own sorted list is already installable (sbg_search7 relies on this).
+  // The part's own sorted list stays on the device; when it is the whole space (nparts == 1) it
+  // IS the list, and phase 2 may follow without sbg_set_list7().
   h->d_list = h->d_sorted;
   h->list_count = keep;
+  h->list_ready = nparts == 1;
   return SBG_OK;
 }
 

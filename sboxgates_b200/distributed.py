@@ -13,6 +13,8 @@ result is the reference's size == 1 result for any number of GPUs.
 The engine is any object with the `LutEngine` part-methods; the CPU tests drive this module over
 `gloo` with an oracle-backed stand-in engine, the product uses `LutEngine` (CUDA) over `nccl`.
 """
+import math
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -33,8 +35,15 @@ def _i64_to_key(v):
 
 
 class DistributedLutSearch:
-    def __init__(self, engine, group=None, device=None):
+    """Sharding pays only when a search is large: below the thresholds every rank simply runs the
+    whole (sub)search itself -- same inputs, same deterministic result, no collective at all."""
+
+    def __init__(self, engine, group=None, device=None, shard_min_tuples5=5e7,
+                 shard_min_tuples7=2e8, shard_min_list=8192):
         self.engine = engine
+        self.shard_min_tuples5 = shard_min_tuples5
+        self.shard_min_tuples7 = shard_min_tuples7
+        self.shard_min_list = shard_min_list
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -44,6 +53,7 @@ class DistributedLutSearch:
                 else torch.device("cpu")
         self.device = device
         self.collectives = 0
+        self.last_phase1_sharded = False
 
     # -- collectives ---------------------------------------------------------------------------
     def _allreduce_min_key(self, key):
@@ -74,18 +84,31 @@ class DistributedLutSearch:
     # -- searches ------------------------------------------------------------------------------
     def search5_sharded(self, order):
         """The current problem's 5-LUT search with a given function order -> raw sbg_result."""
+        n = self.engine.n
+        if self.world == 1 or math.comb(n, 5) < self.shard_min_tuples5:
+            return self.engine.finish5(self.engine.search5_part(0, 1, order), order)
         key = self.engine.search5_part(self.rank, self.world, order)
         key = self._allreduce_min_key(key)
         return self.engine.finish5(key, order)
 
     def search7_sharded(self, outer, middle):
-        local = self.engine.filter7_part(self.rank, self.world)
-        merged = self._allgather_lists(local)
-        # Every rank installs the same merged list; set_list7 sorts it and keeps the first
-        # SBG_LIST_CAP entries (lut.c:316-318 at size == 1).
-        self.engine.set_list7(merged)
-        key = self.engine.decomp7_part(self.rank, self.world, outer, middle)
-        key = self._allreduce_min_key(key)
+        n = self.engine.n
+        self.last_phase1_sharded = not (self.world == 1 or math.comb(n, 7) < self.shard_min_tuples7)
+        if not self.last_phase1_sharded:
+            # phase 1 replicated: every rank builds (and keeps on its device) the same full list
+            count = self.engine.filter7_keep_local()
+        else:
+            local = self.engine.filter7_part(self.rank, self.world)
+            merged = self._allgather_lists(local)
+            # Every rank installs the same merged list; set_list7 sorts it and keeps the first
+            # SBG_LIST_CAP entries (lut.c:316-318 at size == 1).
+            self.engine.set_list7(merged)
+            count = min(len(merged), SBG_LIST_CAP)
+        if self.world == 1 or count < self.shard_min_list:
+            key = self.engine.decomp7_part(0, 1, outer, middle)
+        else:
+            key = self.engine.decomp7_part(self.rank, self.world, outer, middle)
+            key = self._allreduce_min_key(key)
         return self.engine.finish7(key, outer, middle)
 
     def search_5lut(self, tables, target, mask, inbits, rng):

@@ -192,6 +192,13 @@ class LutEngine:
                                               out.ctypes.data_as(native.u64p), C.byref(cnt)))
         return out[:cnt.value].copy()
 
+    def filter7_keep_local(self):
+        """Phase 1 over the whole space on this device; the sorted, capped list stays in HBM as the
+        installed list.  Returns its length."""
+        cnt = C.c_int()
+        self._check(self.lib.sbg_filter7_part(self._h, 0, 1, None, C.byref(cnt)))
+        return cnt.value
+
     def set_list7(self, packed):
         packed, pp = _u64(packed)
         self._check(self.lib.sbg_set_list7(self._h, pp, int(packed.shape[0])))

@@ -25,6 +25,7 @@ class OracleEngine:
         self.target = np.ascontiguousarray(target, dtype=np.uint64)
         self.mask = np.ascontiguousarray(mask, dtype=np.uint64)
         self.inbits = list(inbits)
+        self.n = self.tables.shape[0]
         self.list = None
 
     def search5_part(self, part, nparts, order):
@@ -55,6 +56,10 @@ class OracleEngine:
         lst, _ = S.oracle_filter7(self.tables, self.target, self.mask, self.inbits)
         mine = [pack_tuple7(t) for i, t in enumerate(lst.tolist()) if i % nparts == part]
         return np.array(mine, dtype=np.uint64)
+
+    def filter7_keep_local(self):
+        self.set_list7(self.filter7_part(0, 1))
+        return len(self.list)
 
     def set_list7(self, packed):
         self.list = np.sort(np.asarray(packed, dtype=np.uint64))[:100000]
@@ -108,13 +113,14 @@ def _cases():
     return out
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, force_shard=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         results = []
-        drv = DistributedLutSearch(OracleEngine())
+        kw = dict(shard_min_tuples5=0, shard_min_tuples7=0, shard_min_list=0) if force_shard else {}
+        drv = DistributedLutSearch(OracleEngine(), **kw)
         for tabs, tgt, mask, inb in _cases():
             for which in (5, 7):
                 rng = Xorshift1024(np.random.RandomState(9).bytes(128))
@@ -134,12 +140,13 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_search_equals_single_rank_oracle(world):
+@pytest.mark.parametrize("world,force_shard", [(2, True), (3, True), (2, False)])
+def test_sharded_search_equals_single_rank_oracle(world, force_shard):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, force_shard))
+             for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=300) for _ in range(world)]
@@ -155,5 +162,8 @@ def test_sharded_search_equals_single_rank_oracle(world):
             want.append((which, found, ret, int(rng.draws)))
     for rank, results, collectives in got:
         assert results == want, rank               # every rank holds the same, correct answer
-        # 1 all-reduce per 5-LUT; per 7-LUT 1 count gather (+1 list gather if any hit) + 1 all-reduce
-        assert len(_cases()) * 3 <= collectives <= len(_cases()) * 4
+        if force_shard:
+            # 1 all-reduce per 5-LUT; per 7-LUT 1 count gather (+1 list gather if any hit) + 1 all-reduce
+            assert len(_cases()) * 3 <= collectives <= len(_cases()) * 4
+        else:
+            assert collectives == 0   # small searches are replicated, not sharded
