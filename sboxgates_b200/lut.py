@@ -106,6 +106,7 @@ class LutEngine:
             raise NativeLibraryError("sbg_create(device=%d): %s" % (device, msg))
         self.device = device
         self.n = 0
+        self._slot_n = {}
         if stream is not None:
             self.set_stream(stream)
 
@@ -145,6 +146,7 @@ class LutEngine:
         ib = np.full(8, -1, dtype=np.int8)
         ib[:len(inbits)] = inbits
         self.n = tables.shape[0]
+        self._slot_n[0] = self.n
         self._check(self.lib.sbg_load_problem(self._h, tp, self.n, gp, mp,
                                               ib.ctypes.data_as(native.i8p)))
 
@@ -157,9 +159,11 @@ class LutEngine:
         ib[:len(inbits)] = inbits
         self._check(self.lib.sbg_stage_problem(self._h, slot, tp, tables.shape[0], gp, mp,
                                                ib.ctypes.data_as(native.i8p)))
+        self._slot_n[slot] = tables.shape[0]
 
     def use(self, slot):
         self._check(self.lib.sbg_use_problem(self._h, slot))
+        self.n = self._slot_n[slot]
 
     # -- whole searches ------------------------------------------------------------------------
     def search5(self, func_order):
