@@ -291,21 +291,30 @@ int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_ctas) {
   const int m = popcount256(h->mask);
   const uint64_t tickets = (h_binom[n - 3][4] + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
-#define SBG_LAUNCH_PM(NWV)                                                                     \
+#define SBG_LAUNCH_PM(NWV, WV)                                                                 \
   {                                                                                            \
     const size_t smem = filter_pm_smem<NWV>(n, m);                                             \
-    int grid = grid_for(h, k_filter7_pm<NWV>, smem, tickets);                                  \
+    int grid = grid_for(h, k_filter7_pm<NWV, WV>, smem, tickets);                              \
     if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
     uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, 4);                   \
     if (max_ctas > 0) bsz = 1;                                                                 \
-    k_filter7_pm<NWV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, cap, \
-        part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);                             \
+    k_filter7_pm<NWV, WV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, \
+        cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);                        \
   }
-  switch (h->nw) {
-    case 1: SBG_LAUNCH_PM(1) break;
-    case 2: SBG_LAUNCH_PM(2) break;
-    case 4: SBG_LAUNCH_PM(4) break;
-    default: SBG_LAUNCH_PM(8) break;
+  if (n <= 32) {  // one word of candidate gates per pass
+    switch (h->nw) {
+      case 1: SBG_LAUNCH_PM(1, 1) break;
+      case 2: SBG_LAUNCH_PM(2, 1) break;
+      case 4: SBG_LAUNCH_PM(4, 1) break;
+      default: SBG_LAUNCH_PM(8, 1) break;
+    }
+  } else {
+    switch (h->nw) {
+      case 1: SBG_LAUNCH_PM(1, 2) break;
+      case 2: SBG_LAUNCH_PM(2, 2) break;
+      case 4: SBG_LAUNCH_PM(4, 2) break;
+      default: SBG_LAUNCH_PM(8, 2) break;
+    }
   }
 #undef SBG_LAUNCH_PM
   h->launches++;

@@ -412,11 +412,12 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
 // cells gives exactly the g for which check_n_lut_possible(7, ...) holds (lut.c:34-66); the vector
 // usually empties after the first cell.  Cost per lane: ~30 instructions per visited position for
 // up to 64 candidate g, against ~100 per (pair, cell) in k_sweep.
-template <int NW>
+// W = 32-bit words of candidate gates handled per pass: 1 when n <= 32, else 2.
+template <int NW, int W>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
     int nparts, unsigned long long list_cap, int batch) {
-  constexpr int P = 4, K = 7, NC = 16, W = 2;
+  constexpr int P = 4, K = 7, NC = 16;
   extern __shared__ uint32_t smem[];
   const int n = prob->n;
   const int m = prob->m;
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
           tf[w] = s_tabs[w * npad + gf];
         }
         // windows of 64 candidate gates g; the first window that can hold a g > last + 2
-        for (int wb = ((last + 3) >> 5) & ~(W - 1); wb < ngw; wb += W) {
+        for (int wb = ((last + 3) >> 5) & ~(W - 1); wb < ((n + 31) >> 5); wb += W) {
           uint32_t V[W];
 #pragma unroll
           for (int j = 0; j < W; j++) {
@@ -536,7 +537,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
             if (g0 == 0) v &= ~inmask;
             V[j] = lane_ok ? v : 0u;
           }
-          bool alive = (V[0] | V[1]) != 0;
+          bool alive = false;
+#pragma unroll
+          for (int j = 0; j < W; j++) alive |= V[j] != 0;
           for (int cj = 0; cj < mc; cj++) {
             if (!__any_sync(kFull, alive)) break;
             uint32_t a_and[4][W], a_or[4][W];
@@ -558,15 +561,23 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 const int p = w * 32 + j;
                 const uint32_t tp = (T[w] >> j) & 1u;
                 const uint32_t pk = (((te[w] >> j) & 1u) << 1) | ((tf[w] >> j) & 1u);
-                const uint2 x = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
+                uint32_t x[W];
+                if (W == 2) {
+                  const uint2 xx = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
+                  x[0] = xx.x;
+                  x[W - 1] = xx.y;
+                } else {
+                  x[0] = s_xr[p * ngw + wb];
+                }
                 if (tp) has1 |= 1u << pk; else has0 |= 1u << pk;
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   const uint32_t mk = (pk == (uint32_t)k) ? 0xffffffffu : 0u;
-                  a_and[k][0] &= x.x | ~mk;
-                  a_and[k][1] &= x.y | ~mk;
-                  a_or[k][0] |= x.x & mk;
-                  a_or[k][1] |= x.y & mk;
+#pragma unroll
+                  for (int jw = 0; jw < W; jw++) {
+                    a_and[k][jw] &= x[jw] | ~mk;
+                    a_or[k][jw] |= x[jw] & mk;
+                  }
                 }
               }
             }
@@ -574,14 +585,18 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 #pragma unroll
             for (int k = 0; k < 4; k++) {
               if ((both >> k) & 1u) {
-                V[0] &= a_and[k][0] | ~a_or[k][0];
-                V[1] &= a_and[k][1] | ~a_or[k][1];
+#pragma unroll
+                for (int jw = 0; jw < W; jw++) V[jw] &= a_and[k][jw] | ~a_or[k][jw];
               }
             }
-            alive = (V[0] | V[1]) != 0;
+            alive = false;
+#pragma unroll
+            for (int jw = 0; jw < W; jw++) alive |= V[jw] != 0;
           }
           // emit every surviving g of every lane
-          const int cnt = __popc(V[0]) + __popc(V[1]);
+          int cnt = 0;
+#pragma unroll
+          for (int jw = 0; jw < W; jw++) cnt += __popc(V[jw]);
           int incl = cnt;
 #pragma unroll
           for (int d = 1; d < 32; d <<= 1) {

@@ -150,3 +150,85 @@ def test_planted_7lut_large(engine):
         engine.set_list7(np.concatenate(parts[::-1]))
         keys = [engine.decomp7_part(p, 4, outer, middle) for p in range(4)]
         assert min(keys) == res.key
+
+
+def _fresh_engine(monkeypatch, **env):
+    """A new handle created under the given environment (the library reads its tuning knobs when a
+    handle is created / on first use)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return sb.LutEngine(0)
+
+
+def test_paths_agree(engine):
+    """The one-call search (sbg_search7: on-device sort, single synchronisation) and the
+    step-by-step one (filter part -> list -> decomposition part -> finish) return the same result;
+    so do short lists (on-device bitonic sort) and long ones (radix sort)."""
+    sbox = S.rijndael_sbox()
+    rs = np.random.RandomState(5)
+    for n, fixed in [(14, [(0, 1)]), (20, [(1, 0), (6, 1)]), (28, [(0, 0), (2, 1), (5, 0)]),
+                     (36, [(3, 1), (4, 1), (7, 0)]), (33, [])]:
+        tabs = S.synthetic_state(n, seed=700 + n)
+        mask = S.mux_mask(fixed)
+        inb = [b for b, _ in fixed]
+        tgt = S.sbox_target(sbox, int(rs.randint(0, 8)))
+        seed = rs.bytes(128)
+        outer, middle = sb.shuffled_orders7(Xorshift1024(seed))
+        engine.load(tabs, tgt, mask, inb)
+        whole = engine.search7(outer, middle)
+        count = engine.filter7_keep_local()
+        key = engine.decomp7_part(0, 1, outer, middle)
+        step = engine.finish7(key, outer, middle)
+        assert (whole.found, whole.key, list(whole.gates), whole.func_inner, whole.inner_seen) == \
+            (step.found, step.key, list(step.gates), step.func_inner, step.inner_seen)
+        assert whole.tuples_feasible == count
+
+
+def test_sweep_and_position_major_kernels_agree(engine):
+    """Phase 1 has two implementations (bitmap sweep k_sweep<NW,5>, position-major k_filter7_pm);
+    their hit lists must be identical."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path[:0]=[%r, %r]\n"
+        "import _support as S, sboxgates_b200 as sb\n"
+        "eng = sb.LutEngine(0); sbox = S.rijndael_sbox(); out = []\n"
+        "for n, fixed in [(18, []), (24, [(0,1)]), (30, [(1,0),(4,1)]), (40, [(2,1),(3,0),(6,1)]), (44, [(5, 1)])]:\n"
+        "    eng.load(S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed])\n"
+        "    out.append(eng.filter7_part(0, 1).tolist())\n"
+        "import json; print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
+    lists = {}
+    for mode in ("pm", "sweep"):
+        env = dict(os.environ, SBG_FILTER=mode)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                             check=True)
+        lists[mode] = res.stdout.strip().splitlines()[-1]
+    assert lists["pm"] == lists["sweep"]
+    import json
+    assert sum(len(x) for x in json.loads(lists["pm"])) > 0
+
+
+def test_hit_buffer_overflow_is_retried(monkeypatch):
+    """With a tiny hit buffer phase 1 overflows; the bounded-parallelism retry must still deliver
+    the exact list (first SBG_LIST_CAP feasible tuples in lexicographic order)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path[:0]=[%r, %r]\n"
+        "import _support as S, sboxgates_b200 as sb\n"
+        "eng = sb.LutEngine(0); sbox = S.rijndael_sbox()\n"
+        "tabs = S.synthetic_state(48, seed=48); mask = S.mux_mask([(0,1),(5,0),(3,1)])\n"
+        "eng.load(tabs, S.sbox_target(sbox, 0), mask, [0,5,3])\n"
+        "lst = eng.filter7_part(0, 1)\n"
+        "import hashlib; print(len(lst), hashlib.sha1(lst.tobytes()).hexdigest())\n"
+        % (S.ROOT, os.path.join(S.ROOT, "tests")))
+    outs = []
+    for cap in ("", "200000"):
+        env = dict(os.environ)
+        if cap:
+            env["SBG_HITS_CAP"] = cap
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                             check=True)
+        outs.append(res.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1]
+    assert int(outs[0].split()[0]) == 100000   # the case really hits the cap
