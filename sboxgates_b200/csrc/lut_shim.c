@@ -22,14 +22,17 @@ _Static_assert(sizeof(sbg_state) == 32032, "state must be 32,032 bytes (state.h:
 static sbg_handle *g_handle = NULL;
 static uint64_t g_calls[2] = {0, 0};
 static double g_seconds[2] = {0.0, 0.0};
+static double g_kernel_ms[4] = {0.0, 0.0, 0.0, 0.0}; /* search5, filter7, sort, decomp7 */
 
 static void shim_exit(void) {
   if (g_handle != NULL) {
     if (getenv("SBG_SHIM_STATS") != NULL) {
       fprintf(stderr, "[sbg] search_5lut: %llu calls %.3f s; search_7lut: %llu calls %.3f s; "
-          "%llu kernel launches\n", (unsigned long long)g_calls[0], g_seconds[0],
+          "%llu kernel launches; kernel time: search5 %.3f s, filter7 %.3f s, sort %.3f s, "
+          "decomp7 %.3f s\n", (unsigned long long)g_calls[0], g_seconds[0],
           (unsigned long long)g_calls[1], g_seconds[1],
-          (unsigned long long)sbg_launch_count(g_handle));
+          (unsigned long long)sbg_launch_count(g_handle), 1e-3 * g_kernel_ms[0],
+          1e-3 * g_kernel_ms[1], 1e-3 * g_kernel_ms[2], 1e-3 * g_kernel_ms[3]);
     }
     sbg_destroy(g_handle);
     g_handle = NULL;
@@ -115,6 +118,7 @@ bool search_5lut(const sbg_state st, const sbg_ttable target, const sbg_ttable m
   }
   g_calls[0]++;
   g_seconds[0] += now() - t0;
+  g_kernel_ms[0] += sbg_last_kernel_ms(h, 0);
   return res.found != 0;
 }
 
@@ -155,6 +159,7 @@ bool search_7lut(const sbg_state st, const sbg_ttable target, const sbg_ttable m
   }
   g_calls[1]++;
   g_seconds[1] += now() - t0;
+  for (int i = 1; i < 4; i++) g_kernel_ms[i] += sbg_last_kernel_ms(h, i);
   return res.found != 0;
 }
 

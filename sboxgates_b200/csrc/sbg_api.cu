@@ -431,15 +431,21 @@ int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
 
 void build_params7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle_order) {
   DevParams7 *p = h->h_par7;
-  memset(p, 0, sizeof(*p));
-  for (int pos = 0; pos < 256; pos++) p->pos_outer[outer_order[pos]] = (uint8_t)pos;
-  for (int pm = 0; pm < 256; pm++) {
-    const uint32_t f = middle_order[pm];
-    for (uint32_t s = 0; s < 16; s++) {
-      p->lo[s * 16 + (f & 15u & s)][pm >> 5] |= 1u << (pm & 31);
-      p->hi[s * 16 + ((f >> 4) & s)][pm >> 5] |= 1u << (pm & 31);
-    }
+  for (int pos = 0; pos < 256; pos++) {
+    p->pos_outer[outer_order[pos]] = (uint8_t)pos;
+    p->pos_middle[middle_order[pos]] = (uint8_t)pos;
   }
+}
+
+// Bytes of the per-call block that travel host -> device: control words + the two position tables
+// (DevParams7::minpos3 is built on the device by k_prepare7).
+constexpr size_t kCallUploadBytes = offsetof(sbg_handle::DevCall, par) + offsetof(DevParams7, minpos3);
+
+int launch_prepare7(sbg_handle *h) {
+  k_prepare7<<<1, 1024, 0, h->stream>>>(h->d_par7);
+  h->launches++;
+  SBG_CUDA(h, cudaGetLastError());
+  return SBG_OK;
 }
 
 int run_decomp7(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
@@ -449,9 +455,10 @@ int run_decomp7(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
   h->ms[3] = 0.f;
   if (h->list_count == 0) return SBG_OK;
   build_params7(h, outer_order, middle_order);
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_par7, h->h_par7, sizeof(DevParams7), cudaMemcpyHostToDevice,
-      h->stream));
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_par7, h->h_par7, offsetof(DevParams7, minpos3),
+      cudaMemcpyHostToDevice, h->stream));
   if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+  if ((rc = launch_prepare7(h)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[4], h->stream);
   if ((rc = launch_decomp7(h, part, nparts)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[5], h->stream);
@@ -983,8 +990,9 @@ int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle
   memset(c, 0, sizeof(*c));
   c->best = ~0ull;
   c->stop_ticket = ~0ull;
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_call, h->h_call, sizeof(sbg_handle::DevCall),
-      cudaMemcpyHostToDevice, h->stream));
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_call, h->h_call, kCallUploadBytes, cudaMemcpyHostToDevice,
+      h->stream));
+  if ((rc = launch_prepare7(h)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[0], h->stream);
   if (use_position_major(h)) {
     if ((rc = launch_filter7_pm(h, 0, 1, 0)) != SBG_OK) return rc;

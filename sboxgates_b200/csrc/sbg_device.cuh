@@ -56,14 +56,16 @@ struct DevCtl {
   unsigned int pad;
 };
 
-// Per-call parameters of the 7-LUT decomposition: where each outer function sits in the shuffled
-// outer order, and for the shuffled middle order the 256-bit sets
-//   lo[s*16+a] = { pm : (middle_order[pm] & 0x0f & s) == a },  hi[...] likewise for the high nibble,
-// from which { pm : (middle_order[pm] & S) == A } = lo[S&15, A&15] & hi[S>>4, A>>4].
+// Per-call parameters of the 7-LUT decomposition.  The host supplies where each function sits in
+// the two shuffled orders; k_prepare7 derives from the middle order the table
+//   minpos3[code(S,V)] = min { pm : (middle_order[pm] & S) == V },   V subset of S,
+// indexed in base 3 (digit j = 0: bit j unconstrained, 1: forced 0, 2: forced 1), i.e.
+// code(S,V) = p3(S) + p3(V) with p3(x) = sum of 3^j over the set bits of x.  6,561 entries.
+constexpr int kMinpos3 = 6561;
 struct DevParams7 {
-  uint32_t lo[256][8];
-  uint32_t hi[256][8];
   uint8_t pos_outer[256];
+  uint8_t pos_middle[256];
+  uint8_t minpos3[kMinpos3 + 3];   // device-built; not part of the upload
 };
 
 __constant__ uint64_t c_binom[501][8];   // C(m, r), 0 <= m <= 500, 0 <= r <= 7
@@ -638,6 +640,49 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Builds DevParams7::minpos3 from pos_middle (one CTA).  Entries whose every bit is forced are
+// read off the inverse permutation; an entry with a free bit is the minimum of the two entries that
+// force that bit to 0 / 1, so the table fills level by level in the number of free bits.
+__global__ void __launch_bounds__(1024) k_prepare7(DevParams7 *__restrict__ par) {
+  __shared__ uint8_t mp[kMinpos3 + 3];
+  __shared__ uint8_t posm[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) posm[i] = par->pos_middle[i];
+  constexpr int kPer = (kMinpos3 + 1023) / 1024;
+  int nfree[kPer], wfree[kPer], forced[kPer];
+#pragma unroll
+  for (int t = 0; t < kPer; t++) {
+    const int e = threadIdx.x + t * 1024;
+    int f = 0, wgt = 0, v = 0, rest = e, p3 = 1;
+    for (int j = 0; j < 8; j++) {
+      const int d = rest % 3;
+      rest /= 3;
+      if (d == 0) {
+        if (f == 0) wgt = p3;
+        f++;
+      } else if (d == 2) {
+        v |= 1 << j;
+      }
+      p3 *= 3;
+    }
+    nfree[t] = e < kMinpos3 ? f : -1;
+    wfree[t] = wgt;
+    forced[t] = v;
+  }
+  __syncthreads();
+  for (int level = 0; level <= 8; level++) {
+#pragma unroll
+    for (int t = 0; t < kPer; t++) {
+      if (nfree[t] == level) {
+        const int e = threadIdx.x + t * 1024;
+        mp[e] = level == 0 ? posm[forced[t]] : min(mp[e + wfree[t]], mp[e + 2 * wfree[t]]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) par->minpos3[i] = mp[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Ordering the phase-1 hits (lut.c:329-349 concatenates per-rank lists in rank order, which at
 // size 1 is lexicographic order).  Short lists -- the common case -- are sorted by one CTA with a
 // bitonic network in shared memory, the count being read on the device so that phase 2 can be
@@ -746,9 +791,10 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
     DevCtl *__restrict__ ctl, const DevParams7 *__restrict__ par, const uint64_t *__restrict__ list,
     unsigned int count, int part, int nparts) {
   extern __shared__ uint32_t smem[];
-  __shared__ uint32_t s_lo[256 * 8];
-  __shared__ uint32_t s_hi[256 * 8];
+  __shared__ uint8_t s_minpos[kMinpos3 + 3];
+  __shared__ uint16_t s_p3[256];
   __shared__ uint8_t s_pos[256];
+  __shared__ uint8_t s_fo[kWarpsPerCta][256];
   __shared__ uint32_t s_H[kWarpsPerCta][24];
 
   if (count == 0xffffffffu) {  // list produced on the device by k_sort_small
@@ -766,11 +812,16 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
 
-  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
-    s_lo[i] = (&par->lo[0][0])[i];
-    s_hi[i] = (&par->hi[0][0])[i];
+  for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_minpos[i] = par->minpos3[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_pos[i] = par->pos_outer[i];
+    int p3 = 0, w3 = 1;
+    for (int j = 0; j < 8; j++) {
+      if ((i >> j) & 1) p3 += w3;
+      w3 *= 3;
+    }
+    s_p3[i] = (uint16_t)p3;
   }
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = par->pos_outer[i];
   stage_tables(s_tabs, prob, NW, npad);
 
   uint32_t T[NW], M[NW];
@@ -862,47 +913,79 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
       if (lane < 8) surv[lane] = my_surv;
       __syncwarp();
 
+      // Stage 2, one lane per surviving outer function.  First compact the survivors.
+      uint8_t *fo_list = s_fo[warp];
+      int ns = 0;
+#pragma unroll
+      for (int hi = 0; hi < 8; hi++) {
+        const uint32_t sv = surv[hi];
+        if ((sv >> lane) & 1u) fo_list[ns + __popc(sv & lanemask_lt())] = (uint8_t)(hi * 32 + lane);
+        ns += __popc(sv);
+      }
+      __syncwarp();
+
       const int k0 = c_j_first_k[j];
       const int nrows = c_j_rows[j];
       for (int row = 0; row < nrows && !found; row++) {
         const int k = k0 + row;
         const int b = c_row_b[k];
         uint32_t best_local = 0xffffffffu;
-        for (int hi = 0; hi < 8; hi++) {
-          uint32_t s = surv[hi];
-          while (s != 0) {
-            const int lb = __ffs(s) - 1;
-            s &= s - 1;
-            const int fo = hi * 32 + lb;
-            uint32_t r1 = 0, r0 = 0;
+        for (int i0 = 0; i0 < ns; i0 += 32) {
+          const bool have = i0 + lane < ns;
+          const int fo = have ? fo_list[i0 + lane] : 0;
+          uint32_t r1 = 0, r0 = 0;
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              if ((fo >> u) & 1) r1 |= W[u]; else r0 |= W[u];
-            }
-            // Lane = (constraint ci = (x, z), word w of the 256-bit set over middle positions).
-            const int ci = lane >> 3;
-            const int w = lane & 7;
+          for (int u = 0; u < 8; u++) {
+            if ((fo >> u) & 1) r1 |= W[u]; else r0 |= W[u];
+          }
+          // The four inner cells (x, g): A = middle patterns with a masked 1, B = with a masked 0.
+          // If both are non-empty, fm must send A to one value and B to the other: fm & S in {A, B}.
+          uint32_t cs[4], ca[4], cb[4];
+#pragma unroll
+          for (int ci = 0; ci < 4; ci++) {
             const uint32_t R = (ci & 2) ? r1 : r0;
             const uint32_t A = compress16(R & 0xffffu, b, ci & 1);
             const uint32_t B = compress16(R >> 16, b, ci & 1);
-            uint32_t m = 0xffffffffu;
-            if (A != 0 && B != 0) {
-              // fm must send the v's of A to one value and those of B to the other.
-              const uint32_t S = A | B;
-              const uint32_t sl = (S & 15u) * 16u, sh = (S >> 4) * 16u;
-              m = (s_lo[(sl + (A & 15u)) * 8 + w] & s_hi[(sh + (A >> 4)) * 8 + w])
-                  | (s_lo[(sl + (B & 15u)) * 8 + w] & s_hi[(sh + (B >> 4)) * 8 + w]);
-            }
-            m &= __shfl_xor_sync(kFull, m, 8);
-            m &= __shfl_xor_sync(kFull, m, 16);
-            const uint32_t nz = __ballot_sync(kFull, m != 0) & 0xffu;
-            if (nz != 0) {
-              const int w0 = __ffs(nz) - 1;
-              const uint32_t mw = __shfl_sync(kFull, m, w0);
-              const uint32_t pm = (uint32_t)w0 * 32u + (uint32_t)(__ffs(mw) - 1);
-              best_local = min(best_local, ((uint32_t)s_pos[fo] << 8) | pm);
+            const bool act = A != 0 && B != 0;
+            cs[ci] = act ? (A | B) : 0u;   // inactive: empty support, both choices identical
+            ca[ci] = act ? A : 0u;
+            cb[ci] = act ? B : 0u;
+          }
+          // Combine constraints 0,1 and 2,3 (4 choices each), then cross the two halves; a
+          // combination is consistent iff its forced values agree wherever supports overlap.
+          uint32_t hs[2], hv[2][4];
+          bool hok[2][4];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            const int i = 2 * h2;
+            hs[h2] = cs[i] | cs[i + 1];
+            const uint32_t ov = cs[i] & cs[i + 1];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              const uint32_t v0 = (c & 1) ? cb[i] : ca[i];
+              const uint32_t v1 = (c & 2) ? cb[i + 1] : ca[i + 1];
+              hok[h2][c] = ((v0 ^ v1) & ov) == 0;
+              hv[h2][c] = v0 | v1;
             }
           }
+          const uint32_t S = hs[0] | hs[1];
+          const uint32_t ov = hs[0] & hs[1];
+          const uint32_t p3s = s_p3[S];
+          uint32_t best_pm = 256;
+#pragma unroll
+          for (int c0 = 0; c0 < 4; c0++) {
+#pragma unroll
+            for (int c1 = 0; c1 < 4; c1++) {
+              const bool ok2 = hok[0][c0] && hok[1][c1] && ((hv[0][c0] ^ hv[1][c1]) & ov) == 0;
+              if (ok2) {
+                const uint32_t V = hv[0][c0] | hv[1][c1];
+                best_pm = min(best_pm, (uint32_t)s_minpos[p3s + s_p3[V]]);
+              }
+            }
+          }
+          uint32_t cand = 0xffffffffu;
+          if (have && best_pm < 256) cand = ((uint32_t)s_pos[fo] << 8) | best_pm;
+          best_local = min(best_local, __reduce_min_sync(kFull, cand));
         }
         if (best_local != 0xffffffffu) {
           key = (idx << 23) | ((uint64_t)k << 16) | best_local;
