@@ -189,6 +189,7 @@ struct sbg_handle {
 namespace {
 
 constexpr int kSlots = SBG_PROBLEM_SLOTS;
+constexpr size_t kPerPrefixMax = SBG_LIST_CAP + 32 * 512;  // hits one prefix can emit
 constexpr size_t kHeadEntries = 1024;  // list entries read back together with the control words
 
 int fail(sbg_handle *h, int code, const char *fmt, ...) {
@@ -252,7 +253,7 @@ uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
 }
 
 template <int P>
-int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
+int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps) {
   const int n = h->n;
   const uint64_t tickets = (h_binom[n - 2][P] + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
@@ -260,11 +261,11 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_ctas) {
   {                                                                                            \
     const size_t smem = sweep_smem<NWV, P>(n);                                                 \
     int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
-    if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
+    if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
     uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, P);                   \
-    if (max_ctas > 0) bsz = 1;                                                                 \
+    if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
-        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);             \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_SWEEP(1) break;
@@ -286,7 +287,7 @@ size_t filter_pm_smem(int n, int m) {
 }
 
 // Position-major phase 1 (k_filter7_pm): work items are 4-gate prefixes.
-int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_ctas) {
+int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
   const int n = h->n;
   const int m = popcount256(h->mask);
   const uint64_t tickets = (h_binom[n - 3][4] + nparts - 1) / nparts;
@@ -295,11 +296,11 @@ int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_ctas) {
   {                                                                                            \
     const size_t smem = filter_pm_smem<NWV>(n, m);                                             \
     int grid = grid_for(h, k_filter7_pm<NWV, WV>, smem, tickets);                              \
-    if (max_ctas > 0) grid = std::min(grid, max_ctas);                                         \
+    if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
     uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, 4);                   \
-    if (max_ctas > 0) bsz = 1;                                                                 \
+    if (max_warps > 0) bsz = 1;                                                                \
     k_filter7_pm<NWV, WV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, \
-        cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz);                        \
+        cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);             \
   }
   if (n <= 32) {  // one word of candidate gates per pass
     switch (h->nw) {
@@ -393,13 +394,13 @@ int sort_hits(sbg_handle *h, uint64_t *d_in, uint64_t *d_out, size_t count) {
 // Phase 1 on this device: leaves the sorted local list (<= SBG_LIST_CAP) in d_sorted.
 int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
   int rc;
-  int max_ctas = 0;
+  int max_warps = 0;
   for (int attempt = 0; attempt < 2; attempt++) {
     if ((rc = reset_ctl(h)) != SBG_OK) return rc;
     cudaEventRecord(h->ev[0], h->stream);
     if (use_position_major(h)) {
-      if ((rc = launch_filter7_pm(h, part, nparts, max_ctas)) != SBG_OK) return rc;
-    } else if ((rc = launch_sweep<5>(h, part, nparts, max_ctas)) != SBG_OK) {
+      if ((rc = launch_filter7_pm(h, part, nparts, max_warps)) != SBG_OK) return rc;
+    } else if ((rc = launch_sweep<5>(h, part, nparts, max_warps)) != SBG_OK) {
       return rc;
     }
     cudaEventRecord(h->ev[1], h->stream);
@@ -409,9 +410,10 @@ int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
     if (attempt == 1) {
       return fail(h, SBG_ERR_OVERFLOW, "7-LUT hit buffer (%zu entries) overflowed", h->hits_cap);
     }
-    // Every prefix contributes at most SBG_LIST_CAP hits, and prefixes are handed out in order:
-    // with w warps in flight the buffer needs (w + 1) * SBG_LIST_CAP entries at most.
-    max_ctas = (int)std::max<size_t>(1, (h->hits_cap / SBG_LIST_CAP - 1) / kWarpsPerCta);
+    // A prefix stops contributing once it has emitted SBG_LIST_CAP hits (checked between chunks of
+    // 32 lanes x <= 500 gates), and prefixes are handed out in order: with w warps in flight the
+    // buffer needs at most (w + 1) * kPerPrefixMax entries.
+    max_warps = (int)std::max<size_t>(1, h->hits_cap / kPerPrefixMax - 1);
   }
   h->swept = h->h_ctl->swept;
   const size_t total = (size_t)h->h_ctl->hit_count;
@@ -653,7 +655,7 @@ int sbg_create(sbg_handle **out, int device) {
   SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
   const char *cap_env = getenv("SBG_HITS_CAP");
   h->hits_cap = cap_env != nullptr ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)32 << 20);
-  if (h->hits_cap < 2 * (size_t)SBG_LIST_CAP) h->hits_cap = 2 * (size_t)SBG_LIST_CAP;
+  if (h->hits_cap < 3 * kPerPrefixMax) h->hits_cap = 3 * kPerPrefixMax;
   SBG_CUDA(h, cudaMalloc(&h->d_hits, h->hits_cap * sizeof(uint64_t)));
   SBG_CUDA(h, cudaMalloc(&h->d_sorted, h->hits_cap * sizeof(uint64_t)));
   SBG_CUDA(h, cudaMallocHost(&h->h_list, (size_t)SBG_LIST_CAP * sizeof(uint64_t)));

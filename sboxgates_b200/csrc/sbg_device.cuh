@@ -146,7 +146,7 @@ template <int NW, int P>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
     unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
-    int batch) {
+    int batch, int max_warps) {
   constexpr int K = P + 2;
   constexpr int NC = 1 << P;
   extern __shared__ uint32_t smem[];
@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
   }
   stage_tables(s_tabs, prob, NW, npad);
+  // overflow retry: only the first max_warps warps work (bounds the hits in flight)
+  if (max_warps > 0 && (int)(blockIdx.x * kWarpsPerCta + warp) >= max_warps) return;
 
   uint32_t T[NW], M[NW];
 #pragma unroll
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
 template <int NW, int W>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
-    int nparts, unsigned long long list_cap, int batch) {
+    int nparts, unsigned long long list_cap, int batch, int max_warps) {
   constexpr int P = 4, K = 7, NC = 16;
   extern __shared__ uint32_t smem[];
   const int n = prob->n;
@@ -435,6 +437,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     s_xr[i] = prob->xr[i / ngw][i % ngw];
   }
   stage_tables(s_tabs, prob, NW, npad);
+  // overflow retry: only the first max_warps warps work (bounds the hits in flight)
+  if (max_warps > 0 && (int)(blockIdx.x * kWarpsPerCta + warp) >= max_warps) return;
 
   uint32_t T[NW], M[NW];
 #pragma unroll
