@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "../../include/sboxgates_b200.h"
 
@@ -564,7 +565,20 @@ int sbg_create(sbg_handle **out, int device) {
         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
   }
   if (device < 0 || device >= ndev) return fail(h, SBG_ERR_ARG, "device %d out of range", device);
+  const bool timing = getenv("SBG_DEBUG_TIMING") != nullptr;
+  auto stamp = [&](const char *what) {
+    static double last = 0.0;
+    if (!timing) return;
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    const double t = ts.tv_sec + 1e-9 * ts.tv_nsec;
+    if (last != 0.0) fprintf(stderr, "[sbg_create] %-28s %.1f ms\n", what, 1e3 * (t - last));
+    last = t;
+  };
+  stamp("start");
   SBG_CUDA(h, cudaSetDevice(device));
+  SBG_CUDA(h, cudaFree(nullptr));
+  stamp("context");
   cudaDeviceProp prop;
   SBG_CUDA(h, cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
@@ -572,7 +586,9 @@ int sbg_create(sbg_handle **out, int device) {
   h->stream = h->own_stream;
   for (int i = 0; i < 8; i++) SBG_CUDA(h, cudaEventCreate(&h->ev[i]));
 
+  stamp("stream+events");
   SBG_CUDA(h, cudaMemcpyToSymbol(c_binom, h_binom, sizeof(h_binom)));
+  stamp("first symbol (module load)");
   {
     // search5: lane = u<<2 | v2, canonical cell bit of slot s is 4-s.
     uint8_t src5[10][32];
@@ -639,6 +655,7 @@ int sbg_create(sbg_handle **out, int device) {
     SBG_CUDA(h, cudaMemcpyToSymbol(c_row_b, row_b, sizeof(row_b)));
   }
 
+  stamp("constant tables");
   SBG_CUDA(h, cudaMalloc(&h->d_slots, sizeof(DevProblem) * kSlots));
   h->d_prob = h->d_slots;
   h->slots = new sbg_handle::HostProblem[kSlots];
@@ -653,6 +670,7 @@ int sbg_create(sbg_handle **out, int device) {
   SBG_CUDA(h, cudaMallocHost(&h->h_head, kHeadEntries * sizeof(uint64_t)));
   SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
   SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
+  stamp("small buffers + pinned");
   const char *cap_env = getenv("SBG_HITS_CAP");
   h->hits_cap = cap_env != nullptr ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)32 << 20);
   if (h->hits_cap < 3 * kPerPrefixMax) h->hits_cap = 3 * kPerPrefixMax;
@@ -664,6 +682,7 @@ int sbg_create(sbg_handle **out, int device) {
       (int)h->hits_cap, 0, 63, h->stream));
   SBG_CUDA(h, cudaMalloc(&h->d_cub, h->cub_bytes));
   SBG_CUDA(h, cudaStreamSynchronize(h->stream));
+  stamp("hit buffers + cub temp");
   return SBG_OK;
 }
 
