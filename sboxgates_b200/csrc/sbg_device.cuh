@@ -190,9 +190,13 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
     }
   };
-  fetch();
+  // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
+  // would be worked on even if the cap was reached meanwhile, doubling the hits in flight.
+  const bool ahead = max_warps == 0;
+  if (ahead) fetch();
   bool warp_finished = false;
   while (!warp_finished) {
+    if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     const unsigned long long stop_at = __shfl_sync(kFull, next_stop, 0);
     if (b == ~0ull) break;
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     if (gb >= nbatches) break;
     const uint64_t t_first = gb * (uint64_t)batch;
     if (P == 3 && t_first > stop_at) break;
-    fetch();
+    if (ahead) fetch();
     const uint64_t t_end = min(t_first + (uint64_t)batch, total);
 
     int pre[P];
@@ -457,14 +461,18 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
       next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
     }
   };
-  fetch();
+  // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
+  // would be worked on even if the cap was reached meanwhile, doubling the hits in flight.
+  const bool ahead = max_warps == 0;
+  if (ahead) fetch();
   for (;;) {
+    if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     if (b == ~0ull) break;
     const uint64_t gb = b * (uint64_t)nparts + (uint64_t)part;
     if (gb >= nbatches) break;
     const uint64_t t_first = gb * (uint64_t)batch;
-    fetch();
+    if (ahead) fetch();
     const uint64_t t_end = min(t_first + (uint64_t)batch, total);
     int pre[P];
     uint64_t unused_rank;

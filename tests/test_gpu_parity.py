@@ -232,3 +232,35 @@ def test_hit_buffer_overflow_is_retried(monkeypatch):
         outs.append(res.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1]
     assert int(outs[0].split()[0]) == 100000   # the case really hits the cap
+
+
+def _max_size_case():
+    rs = np.random.RandomState(500)
+    tabs = S.synthetic_state(500, seed=500)
+    mask = np.zeros(4, dtype=np.uint64)
+    for p in rs.choice(256, 6, replace=False):
+        mask[p >> 6] |= np.uint64(1) << np.uint64(p & 63)
+    # (gate 0 must not be excluded: the CPU oracle, like the reference, would step through all
+    # C(499,6) tuples that start with it one by one)
+    return rs, tabs, S.sbox_target(S.rijndael_sbox(), 2), mask, [5]
+
+
+def test_maximum_size_state(engine):
+    """MAX_GATES = 500 (state.h:26): 16-word gate vectors, 9-bit packed gate numbers, the 100,000
+    cap reached inside the first prefixes.  Very sparse mask, so most tuples are feasible and both the
+    oracle (asked for the first 3,000 entries only) and the GPU stop early."""
+    rs, tabs, tgt, mask, inb = _max_size_case()
+    want, _ = S.oracle_filter7(tabs, tgt, mask, inb, cap=3000)
+    assert len(want) == 3000
+    engine.load(tabs, tgt, mask, inb)
+    got = engine.filter7_part(0, 1)
+    assert len(got) == 100000 and np.all(got[1:] > got[:-1])
+    assert [sb.lut.unpack_tuple7(p) for p in got[:3000]] == want.tolist()
+    for which in (5, 7):
+        seed = rs.bytes(128)
+        o_rng = S.OrcRng.from_seed(seed)
+        found, ret, _ = S.oracle_search(which, tabs, tgt, mask, inb, o_rng)
+        g_rng = Xorshift1024(seed)
+        res = _run_gpu(engine, (which, tabs, tgt, mask, inb), g_rng)
+        assert (res.found, res.ret, g_rng.draws) == (found, ret, o_rng.draws)
+        assert found
