@@ -135,8 +135,8 @@ def units_of(n, r5, r7):
     """(T, C) units of one state from the two results, as the reference would have enumerated."""
     t = math.comb(n, 5) if not r5.found else int(r5.index) + 1
     c = int(r5.tuples_feasible) * C_PER_5
-    if r5.found:
-        c = max(0, int(r5.tuples_feasible) - 1) * C_PER_5 + r5.ordering * 256 + r5.pos_outer + 1
+    if r5.found:   # candidates of the matching tuple only (earlier feasible tuples are not counted)
+        c = r5.ordering * 256 + r5.pos_outer + 1
     t7 = int(r7.tuples_swept)      # this rank's share; summed over ranks by the caller
     if r7.found:
         c += int(r7.index) * C_PER_7 + r7.ordering * 65536 + r7.pos_outer * 256 + r7.pos_middle + 1

@@ -254,7 +254,7 @@ uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
 }
 
 template <int P>
-int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps) {
+int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 = false) {
   const int n = h->n;
   const uint64_t tickets = (h_binom[n - 2][P] + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
@@ -266,7 +266,8 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps) {
     uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, P);                   \
     if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
-        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
+        emit5);                                                                                \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_SWEEP(1) break;
@@ -471,18 +472,53 @@ int run_decomp7(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
   return SBG_OK;
 }
 
+int launch_decomp5(sbg_handle *h) {
+  const int n = h->n;
+#define SBG_LAUNCH_D5(NWV)                                                                     \
+  {                                                                                            \
+    const size_t smem = decomp_smem<NWV>(n);                                                   \
+    k_decomp5<NWV><<<2 * h->sm_count, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,        \
+        h->d_pos5, h->d_hits);                                                                 \
+  }
+  switch (h->nw) {
+    case 1: SBG_LAUNCH_D5(1) break;
+    case 2: SBG_LAUNCH_D5(2) break;
+    case 4: SBG_LAUNCH_D5(4) break;
+    default: SBG_LAUNCH_D5(8) break;
+  }
+#undef SBG_LAUNCH_D5
+  h->launches++;
+  SBG_CUDA(h, cudaGetLastError());
+  return SBG_OK;
+}
+
+// search_5lut on this part.  Small searches (the bulk of a real run) use two kernels -- sweep that
+// only records feasible tuples, then one warp per recorded tuple -- so that the decomposition of
+// several feasible tuples met by one warp is not serialised; large ones use the fused kernel, whose
+// ordered early exit matters there.  Either way one host synchronisation.
 int run_search5(sbg_handle *h, int part, int nparts, const uint8_t *func_order, uint64_t *key) {
   int rc;
+  static const char *mode_env = getenv("SBG_SEARCH5");
+  const uint64_t two_kernel_max = 4000000;  // C(n,5) up to n = 52
+  bool two = mode_env != nullptr ? strcmp(mode_env, "two") == 0 : h_binom[h->n][5] <= two_kernel_max;
   for (int pos = 0; pos < 256; pos++) h->h_pos5[func_order[pos]] = (uint8_t)pos;
   SBG_CUDA(h, cudaMemcpyAsync(h->d_pos5, h->h_pos5, 256, cudaMemcpyHostToDevice, h->stream));
-  if ((rc = reset_ctl(h)) != SBG_OK) return rc;
-  cudaEventRecord(h->ev[6], h->stream);
-  if ((rc = launch_sweep<3>(h, part, nparts, 0)) != SBG_OK) return rc;
-  cudaEventRecord(h->ev[7], h->stream);
-  if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+  for (;;) {
+    if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[6], h->stream);
+    if ((rc = launch_sweep<3>(h, part, nparts, 0, two)) != SBG_OK) return rc;
+    if (two && (rc = launch_decomp5(h)) != SBG_OK) return rc;
+    cudaEventRecord(h->ev[7], h->stream);
+    if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+    if (two && h->h_ctl->overflow != 0) {
+      two = false;   // more feasible tuples than the buffer holds: let the fused kernel do it
+      continue;
+    }
+    break;
+  }
   h->ms[0] = elapsed(h, 6, 7);
   h->swept = h->h_ctl->swept;
-  h->feasible = h->h_ctl->feasible;
+  h->feasible = two ? h->h_ctl->hit_count : h->h_ctl->feasible;
   *key = h->h_ctl->best;
   return SBG_OK;
 }

@@ -131,6 +131,64 @@ __device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// search_5lut's inner loops for ONE feasible 5-tuple (lut.c:189-230), whole warp: the 10 orderings x
+// 256 outer functions decided from the tuple's 32-cell summary H1/H0 (cells that contain a masked
+// 1 / a masked 0 of the target).  Returns the first (ordering, position in the shuffled function
+// order) that decomposes, as k<<8 | pos, or 0xffffffff.
+template <int NW>
+__device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int npad, const int *g,
+    const uint32_t *T, const uint32_t *M, int lane, const uint8_t *s_pos) {
+  uint32_t ones = 0, zeros = 0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    uint32_t tt = M[w];
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      const uint32_t tv = s_tabs[w * npad + g[i]];
+      tt &= ((lane >> (4 - i)) & 1) ? tv : ~tv;
+    }
+    ones |= tt & T[w];
+    zeros |= tt & ~T[w];
+  }
+  const uint32_t H1 = __ballot_sync(kFull, ones != 0);
+  const uint32_t H0 = __ballot_sync(kFull, zeros != 0);
+  for (int k = 0; k < 10; k++) {
+    const int s = c_src5[k][lane];
+    const uint32_t b1 = __ballot_sync(kFull, (H1 >> s) & 1u);
+    const uint32_t b0 = __ballot_sync(kFull, (H0 >> s) & 1u);
+    // wv(u): bits 0-3 = inner cells (x, d, e) with a masked 1 contributed by outer pattern u,
+    // bits 4-7 = the same for masked 0.
+#define SBG_W5(u) (((b1 >> (4 * (u))) & 0xfu) | (((b0 >> (4 * (u))) & 0xfu) << 4))
+    uint32_t L = 0;
+#pragma unroll
+    for (int u = 0; u < 5; u++) {
+      if ((lane >> u) & 1) L |= SBG_W5(u);
+    }
+    uint32_t ok[8];
+#pragma unroll
+    for (int hi = 0; hi < 8; hi++) {
+      uint32_t rr = L;
+      if (hi & 1) rr |= SBG_W5(5);
+      if (hi & 2) rr |= SBG_W5(6);
+      if (hi & 4) rr |= SBG_W5(7);
+      ok[hi] = __ballot_sync(kFull, ((rr & (rr >> 4)) & 0xfu) == 0);
+    }
+#undef SBG_W5
+    // Outer function fo = hi*32+lane maps pattern u to x = bit u of fo; it works iff neither
+    // {u: x=1} nor {u: x=0} merges a masked 1 and a masked 0 into one inner cell.
+    uint32_t best_pos = 256;
+#pragma unroll
+    for (int hi = 0; hi < 8; hi++) {
+      const uint32_t surv = ok[hi] & __brev(ok[7 - hi]);
+      if ((surv >> lane) & 1u) best_pos = min(best_pos, (uint32_t)s_pos[hi * 32 + lane]);
+    }
+    best_pos = __reduce_min_sync(kFull, best_pos);
+    if (best_pos < 256) return ((uint32_t)k << 8) | best_pos;
+  }
+  return 0xffffffffu;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Sweep kernel.  One warp per P-element prefix; lanes take the (f,g) pairs that complete it.
 //   P = 3 (K = 5): search_5lut's loop over C(n,5) (lut.c:174-245), feasibility test and the
 //                  10 x 256 decomposition attempts fused; result = minimum key in ctl->best.
@@ -146,7 +204,7 @@ template <int NW, int P>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
     unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
-    int batch, int max_warps) {
+    int batch, int max_warps, bool emit5) {
   constexpr int K = P + 2;
   constexpr int NC = 1 << P;
   extern __shared__ uint32_t smem[];
@@ -329,74 +387,49 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
         emitted += cnt;
         if (emitted >= list_cap) warp_done = true;
       } else {
+        if (emit5) {
+          // Two-kernel form for small searches: feasible 5-tuples are only recorded here (rank and
+          // packed gates) and decomposed by k_decomp5, one warp per tuple, so that a warp meeting
+          // several of them does not become the kernel's critical path.
+          const int cnt = __popc(fb);
+          unsigned long long base_slot = 0;
+          if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)cnt);
+          base_slot = __shfl_sync(kFull, base_slot, 0);
+          if (alive) {
+            const unsigned long long slot = base_slot + __popc(fb & lanemask_lt());
+            uint64_t packed = 0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) packed = (packed << 9) | (uint64_t)pre[i];
+            packed = (packed << 18) | ((uint64_t)gf << 9) | (uint64_t)gg;
+            if (2 * slot + 1 < hits_cap) {
+              hits[2 * slot] = base_rank + q;
+              hits[2 * slot + 1] = packed;
+            } else {
+              atomicExch(&ctl->overflow, 1u);
+            }
+          }
+          continue;
+        }
         // search_5lut: try the 10 orderings x 256 outer functions on each feasible tuple
-        // (lut.c:189-230) using only its 32-cell summary H1/H0 (cells that contain a masked
-        // 1 / a masked 0 of the target).
+        // (lut.c:189-230), here, one after the other.
         while (fb != 0 && !warp_done) {
           const int src = __ffs(fb) - 1;
           fb &= fb - 1;
-          const int gd = __shfl_sync(kFull, gf, src);
-          const int ge = __shfl_sync(kFull, gg, src);
-          uint32_t ones = 0, zeros = 0;
-#pragma unroll
-          for (int w = 0; w < NW; w++) {
-            uint32_t tt = M[w];
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              const uint32_t tv = s_tabs[w * npad + pre[i]];
-              tt &= ((lane >> (4 - i)) & 1) ? tv : ~tv;
-            }
-            const uint32_t td = s_tabs[w * npad + gd];
-            const uint32_t te = s_tabs[w * npad + ge];
-            tt &= ((lane >> 1) & 1) ? td : ~td;
-            tt &= (lane & 1) ? te : ~te;
-            ones |= tt & T[w];
-            zeros |= tt & ~T[w];
-          }
-          const uint32_t H1 = __ballot_sync(kFull, ones != 0);
-          const uint32_t H0 = __ballot_sync(kFull, zeros != 0);
+          int g5[5];
+          g5[0] = pre[0];
+          g5[1] = pre[1];
+          g5[2] = pre[P > 2 ? 2 : 0];
+          g5[3] = __shfl_sync(kFull, gf, src);
+          g5[4] = __shfl_sync(kFull, gg, src);
           if (lane == 0) atomicAdd(&ctl->feasible, 1ull);
-
-          for (int k = 0; k < 10; k++) {
-            const int s = c_src5[k][lane];
-            const uint32_t b1 = __ballot_sync(kFull, (H1 >> s) & 1u);
-            const uint32_t b0 = __ballot_sync(kFull, (H0 >> s) & 1u);
-            // wv(u): bits 0-3 = inner cells (x, d, e) with a masked 1 contributed by outer
-            // pattern u, bits 4-7 = the same for masked 0.
-#define SBG_W5(u) (((b1 >> (4 * (u))) & 0xfu) | (((b0 >> (4 * (u))) & 0xfu) << 4))
-            uint32_t L = 0;
-#pragma unroll
-            for (int u = 0; u < 5; u++) {
-              if ((lane >> u) & 1) L |= SBG_W5(u);
+          const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos);
+          if (hit != 0xffffffffu) {
+            const uint64_t key = ((base_rank + q0 + src) << 12) | (uint64_t)hit;
+            if (lane == 0) {
+              atomicMin(&ctl->best, (unsigned long long)key);
+              atomicMin(&ctl->stop_ticket, (unsigned long long)gt);
             }
-            uint32_t ok[8];
-#pragma unroll
-            for (int hi = 0; hi < 8; hi++) {
-              uint32_t rr = L;
-              if (hi & 1) rr |= SBG_W5(5);
-              if (hi & 2) rr |= SBG_W5(6);
-              if (hi & 4) rr |= SBG_W5(7);
-              ok[hi] = __ballot_sync(kFull, ((rr & (rr >> 4)) & 0xfu) == 0);
-            }
-#undef SBG_W5
-            // Outer function fo = hi*32+lane maps pattern u to x = bit u of fo; it works iff
-            // neither {u: x=1} nor {u: x=0} merges a masked 1 and a masked 0 into one inner cell.
-            uint32_t best_pos = 256;
-#pragma unroll
-            for (int hi = 0; hi < 8; hi++) {
-              const uint32_t surv = ok[hi] & __brev(ok[7 - hi]);
-              if ((surv >> lane) & 1u) best_pos = min(best_pos, (uint32_t)s_pos[hi * 32 + lane]);
-            }
-            best_pos = __reduce_min_sync(kFull, best_pos);
-            if (best_pos < 256) {
-              const uint64_t key = ((base_rank + q0 + src) << 12) | ((uint64_t)k << 8) | best_pos;
-              if (lane == 0) {
-                atomicMin(&ctl->best, (unsigned long long)key);
-                atomicMin(&ctl->stop_ticket, (unsigned long long)gt);
-              }
-              warp_done = true;
-              break;
-            }
+            warp_done = true;
           }
         }
       }
@@ -405,6 +438,45 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
    }
   }
   if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second kernel of the two-kernel search_5lut: one warp per recorded feasible 5-tuple.
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, const uint64_t *__restrict__ hits) {
+  extern __shared__ uint32_t smem[];
+  __shared__ uint8_t s_pos[256];
+  const unsigned long long count = ctl->hit_count;
+  if (ctl->overflow != 0 || (unsigned long long)blockIdx.x * kWarpsPerCta >= count) return;
+  const int n = prob->n;
+  const int npad = (n + 3) & ~3;
+  uint32_t *s_tabs = smem;
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
+  stage_tables(s_tabs, prob, NW, npad);
+  uint32_t T[NW], M[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    T[w] = prob->T[w];
+    M[w] = prob->M[w];
+  }
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(&ctl->ticket2, 1ull);
+    t = __shfl_sync(kFull, t, 0);
+    if (t >= count) break;
+    const uint64_t rank = hits[2 * t];
+    if ((volatile_load(&ctl->best) >> 12) < rank) continue;  // a smaller combination matched
+    const uint64_t packed = hits[2 * t + 1];
+    int g5[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) g5[i] = (int)((packed >> (9 * (4 - i))) & 0x1ffu);
+    const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos);
+    if (hit != 0xffffffffu && lane == 0) {
+      atomicMin(&ctl->best, (unsigned long long)((rank << 12) | (uint64_t)hit));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
