@@ -362,6 +362,8 @@ def main():
     def timed(resident):
         acc = {"T": 0, "C": 0, "T7": 0, "T7_rep": 0, "ms5": 0.0, "ms_filter": 0.0, "ms_sort": 0.0,
                "ms_decomp": 0.0}
+        sampler = ClockSampler(local_rank)   # samples every 100 ms from the warm-up on
+        sampler.start()
         for s in range(args.warmup):
             if resident:
                 for i, st in enumerate(batches[s]):
@@ -370,9 +372,7 @@ def main():
         launches0 = eng.launches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(args.steps)]
-        sampler = ClockSampler(local_rank)
         barrier()
-        sampler.start()
         t_wall = 0.0
         for s in range(args.steps):
             states = batches[args.warmup + s]

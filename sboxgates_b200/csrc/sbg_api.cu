@@ -155,7 +155,6 @@ struct sbg_handle {
   size_t hits_cap = 0;
   void *d_cub = nullptr;
   size_t cub_bytes = 0;
-  uint64_t *h_list = nullptr;    // pinned, SBG_LIST_CAP entries
   uint32_t list_count = 0;
   bool list_ready = false;
 
@@ -239,9 +238,20 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
 // Prefixes per ticket batch.  One batch costs one global atomic; batches should hold enough pairs
 // to hide its latency (~64 chunks of 32), leave several batches per resident warp, and never hold
 // more work than a warp's fair share (prefixes are dealt heaviest first, so the tail evens out).
-uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
+//
+// The batch size also defines how work is dealt to the parts of a sharded search (part p takes
+// batches p, p + nparts, ...), so it must be the same on every rank: it is a function of the
+// problem and a nominal warp count only, never of the device a rank happens to run on.
+constexpr uint64_t kNominalWarps = 148 * 2 * kWarpsPerCta;
+
+uint64_t pick_batch(uint64_t tickets, int n, int P) {
+  const uint64_t warps = kNominalWarps;
   static const char *env = getenv("SBG_BATCH");
-  if (env != nullptr) return std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+  if (env != nullptr) {
+    uint64_t b = std::max<uint64_t>(1, std::min<uint64_t>(16, strtoull(env, nullptr, 10)));
+    while (b & (b - 1)) b &= b - 1;
+    return b;
+  }
   const int K = P == 4 ? 7 : P + 2;
   // work per ticket in lane-items: (f,g) pairs for the sweeps, (e,f) pairs for the 4-prefix kernel
   const uint64_t total = P == 4 ? h_binom[n - 1][6] : h_binom[n][K];
@@ -250,7 +260,9 @@ uint64_t pick_batch(uint64_t tickets, uint64_t warps, int n, int P) {
   uint64_t b = (64 * 32 + avg_pairs - 1) / avg_pairs;
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, tickets / (warps * 4)));
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, total / (warps * std::max<uint64_t>(1, qmax))));
-  return std::max<uint64_t>(1, std::min<uint64_t>(16, b));
+  b = std::max<uint64_t>(1, std::min<uint64_t>(16, b));
+  while (b & (b - 1)) b &= b - 1;   // power of two: a batch must not straddle two deal blocks
+  return b;
 }
 
 template <int P>
@@ -263,7 +275,7 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
     const size_t smem = sweep_smem<NWV, P>(n);                                                 \
     int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, P);                   \
+    uint64_t bsz = pick_batch(tickets, n, P);                                                  \
     if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
@@ -299,7 +311,7 @@ int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
     const size_t smem = filter_pm_smem<NWV>(n, m);                                             \
     int grid = grid_for(h, k_filter7_pm<NWV, WV>, smem, tickets);                              \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(tickets, (uint64_t)grid * kWarpsPerCta, n, 4);                   \
+    uint64_t bsz = pick_batch(tickets, n, 4);                                                  \
     if (max_warps > 0) bsz = 1;                                                                \
     k_filter7_pm<NWV, WV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, \
         cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);             \
@@ -712,7 +724,6 @@ int sbg_create(sbg_handle **out, int device) {
   if (h->hits_cap < 3 * kPerPrefixMax) h->hits_cap = 3 * kPerPrefixMax;
   SBG_CUDA(h, cudaMalloc(&h->d_hits, h->hits_cap * sizeof(uint64_t)));
   SBG_CUDA(h, cudaMalloc(&h->d_sorted, h->hits_cap * sizeof(uint64_t)));
-  SBG_CUDA(h, cudaMallocHost(&h->h_list, (size_t)SBG_LIST_CAP * sizeof(uint64_t)));
   h->cub_bytes = 0;
   SBG_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, h->cub_bytes, h->d_hits, h->d_sorted,
       (int)h->hits_cap, 0, 63, h->stream));
@@ -732,7 +743,6 @@ void sbg_destroy(sbg_handle *h) {
     cudaFreeHost(h->h_ctl_out); cudaFreeHost(h->h_head);
     cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
     cudaFree(h->d_hits); cudaFree(h->d_sorted); cudaFree(h->d_cub);
-    cudaFreeHost(h->h_list);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->own_stream);
   }

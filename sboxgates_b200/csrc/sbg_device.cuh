@@ -26,6 +26,7 @@ constexpr int kMaxGatesPad = 512;
 constexpr int kThreads = 256;
 constexpr int kWarpsPerCta = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr uint64_t kDeal = 16;  // prefixes per block dealt to one part of a sharded search
 
 struct DevProblem {
   uint32_t tabs[8][kMaxGatesPad];  // [word][gate], compressed + pre-ANDed with the mask
@@ -237,7 +238,6 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   // prefixes: one global atomic per batch, issued one batch ahead so that its latency (and that of
   // the stop-flag read) overlaps the previous batch's work; inside a batch the prefix and the rank
   // of its first combination advance incrementally instead of being unranked again.
-  const uint64_t nbatches = (total + (uint64_t)batch - 1) / (uint64_t)batch;
   unsigned long long swept_local = 0;
   unsigned long long next_b = 0, next_stop = ~0ull;
   auto fetch = [&]() {
@@ -258,9 +258,13 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     const unsigned long long stop_at = __shfl_sync(kFull, next_stop, 0);
     if (b == ~0ull) break;
-    const uint64_t gb = b * (uint64_t)nparts + (uint64_t)part;
-    if (gb >= nbatches) break;
-    const uint64_t t_first = gb * (uint64_t)batch;
+    // Prefixes are dealt to the parts of a sharded search in blocks of kDeal consecutive prefixes
+    // (part p owns blocks p, p + nparts, ...), independently of the batch size, which is a power
+    // of two <= kDeal so that a batch never straddles two blocks.
+    const uint64_t lt = b * (uint64_t)batch;
+    const uint64_t t_first = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
+        + (lt % kDeal);
+    if (t_first >= total) break;
     if (P == 3 && t_first > stop_at) break;
     if (ahead) fetch();
     const uint64_t t_end = min(t_first + (uint64_t)batch, total);
@@ -524,7 +528,6 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   }
   const uint32_t inmask = prob->inmask;
   const uint64_t total = c_binom[n - 3][P];
-  const uint64_t nbatches = (total + (uint64_t)batch - 1) / (uint64_t)batch;
   unsigned long long swept_local = 0;
   unsigned long long next_b = 0;
   auto fetch = [&]() {
@@ -541,9 +544,10 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     if (b == ~0ull) break;
-    const uint64_t gb = b * (uint64_t)nparts + (uint64_t)part;
-    if (gb >= nbatches) break;
-    const uint64_t t_first = gb * (uint64_t)batch;
+    const uint64_t lt = b * (uint64_t)batch;   // dealt in blocks of kDeal prefixes, see k_sweep
+    const uint64_t t_first = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
+        + (lt % kDeal);
+    if (t_first >= total) break;
     if (ahead) fetch();
     const uint64_t t_end = min(t_first + (uint64_t)batch, total);
     int pre[P];
@@ -724,46 +728,29 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Builds DevParams7::minpos3 from pos_middle (one CTA).  Entries whose every bit is forced are
-// read off the inverse permutation; an entry with a free bit is the minimum of the two entries that
-// force that bit to 0 / 1, so the table fills level by level in the number of free bits.
+// Builds DevParams7::minpos3 from pos_middle (one CTA): entry (S,V) is the minimum, over the
+// completions of V on the bits outside S, of that function's position -- 4^8 lookups in all, no
+// synchronisation between entries.
 __global__ void __launch_bounds__(1024) k_prepare7(DevParams7 *__restrict__ par) {
-  __shared__ uint8_t mp[kMinpos3 + 3];
   __shared__ uint8_t posm[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) posm[i] = par->pos_middle[i];
-  constexpr int kPer = (kMinpos3 + 1023) / 1024;
-  int nfree[kPer], wfree[kPer], forced[kPer];
+  __syncthreads();
+  for (int e = threadIdx.x; e < kMinpos3; e += blockDim.x) {
+    uint32_t free_bits = 0, forced = 0;
+    int rest = e;
 #pragma unroll
-  for (int t = 0; t < kPer; t++) {
-    const int e = threadIdx.x + t * 1024;
-    int f = 0, wgt = 0, v = 0, rest = e, p3 = 1;
     for (int j = 0; j < 8; j++) {
       const int d = rest % 3;
       rest /= 3;
-      if (d == 0) {
-        if (f == 0) wgt = p3;
-        f++;
-      } else if (d == 2) {
-        v |= 1 << j;
-      }
-      p3 *= 3;
+      if (d == 0) free_bits |= 1u << j;
+      if (d == 2) forced |= 1u << j;
     }
-    nfree[t] = e < kMinpos3 ? f : -1;
-    wfree[t] = wgt;
-    forced[t] = v;
-  }
-  __syncthreads();
-  for (int level = 0; level <= 8; level++) {
-#pragma unroll
-    for (int t = 0; t < kPer; t++) {
-      if (nfree[t] == level) {
-        const int e = threadIdx.x + t * 1024;
-        mp[e] = level == 0 ? posm[forced[t]] : min(mp[e + wfree[t]], mp[e + 2 * wfree[t]]);
-      }
+    uint32_t best = posm[forced];
+    for (uint32_t sub = free_bits; sub != 0; sub = (sub - 1) & free_bits) {
+      best = min(best, (uint32_t)posm[forced | sub]);
     }
-    __syncthreads();
+    par->minpos3[e] = (uint8_t)best;
   }
-  for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) par->minpos3[i] = mp[i];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -220,7 +220,8 @@ def test_hit_buffer_overflow_is_retried(monkeypatch):
         "tabs = S.synthetic_state(48, seed=48); mask = S.mux_mask([(0,1),(5,0),(3,1)])\n"
         "eng.load(tabs, S.sbox_target(sbox, 0), mask, [0,5,3])\n"
         "lst = eng.filter7_part(0, 1)\n"
-        "import hashlib; print(len(lst), hashlib.sha1(lst.tobytes()).hexdigest())\n"
+        "parts = np.sort(np.concatenate([eng.filter7_part(p, 3) for p in range(3)]))[:100000]\n"
+        "import hashlib; print(len(lst), hashlib.sha1(lst.tobytes()).hexdigest(), hashlib.sha1(parts.tobytes()).hexdigest())\n"
         % (S.ROOT, os.path.join(S.ROOT, "tests")))
     outs = []
     for cap in ("", "200000"):
@@ -231,7 +232,9 @@ def test_hit_buffer_overflow_is_retried(monkeypatch):
                              check=True)
         outs.append(res.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1]
-    assert int(outs[0].split()[0]) == 100000   # the case really hits the cap
+    n_hits, whole_hash, parts_hash = outs[0].split()
+    assert int(n_hits) == 100000          # the case really hits the cap
+    assert whole_hash == parts_hash       # three parts (some of them retried) merge to the same list
 
 
 def _max_size_case():
