@@ -252,11 +252,12 @@ uint64_t pick_batch(uint64_t tickets, int n, int P) {
     while (b & (b - 1)) b &= b - 1;
     return b;
   }
-  const int K = P == 4 ? 7 : P + 2;
-  // work per ticket in lane-items: (f,g) pairs for the sweeps, (e,f) pairs for the 4-prefix kernel
-  const uint64_t total = P == 4 ? h_binom[n - 1][6] : h_binom[n][K];
+  // work per ticket in lane-items: (f,g) pairs for the sweeps (P = 3, 5), (e,f) pairs for the
+  // position-major kernel with 4-gate prefixes (P = 4), single f for its 5-gate form (P = 6)
+  const bool pm = P == 4 || P == 6;
+  const uint64_t total = pm ? h_binom[n - 1][6] : h_binom[n][P + 2];
   const uint64_t avg_pairs = std::max<uint64_t>(1, total / std::max<uint64_t>(1, tickets));
-  const uint64_t qmax = h_binom[n - P - (P == 4 ? 1 : 0)][2];
+  const uint64_t qmax = P == 6 ? (uint64_t)std::max(1, n - 7) : h_binom[n - P - (P == 4 ? 1 : 0)][2];
   uint64_t b = (64 * 32 + avg_pairs - 1) / avg_pairs;
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, tickets / (warps * 4)));
   b = std::min<uint64_t>(b, std::max<uint64_t>(1, total / (warps * std::max<uint64_t>(1, qmax))));
@@ -293,28 +294,34 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
   return SBG_OK;
 }
 
-template <int NW>
+template <int NW, int P>
 size_t filter_pm_smem(int n, int m) {
   const int npad = (n + 3) & ~3;
   const int ngw = (((n + 31) >> 5) + 1) & ~1;
-  return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3) + kWarpsPerCta * 16 * NW);
+  return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3) + kWarpsPerCta * (1 << P) * NW);
 }
 
-// Position-major phase 1 (k_filter7_pm): work items are 4-gate prefixes.
-int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
+// Position-major phase 1 (k_filter7_pm): work items are 4- or 5-gate prefixes.  The 5-gate form does
+// half the work per visited position but keeps only n-7-ish lanes of a warp busy, so it is used
+// from n = kPm5MinGates on (measured cross-over, profiles/); SBG_PM_PREFIX=4|5 overrides.
+constexpr int kPm5MinGates = 64;
+
+template <int P>
+int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
   const int n = h->n;
   const int m = popcount256(h->mask);
-  const uint64_t tickets = (h_binom[n - 3][4] + nparts - 1) / nparts;
+  const uint64_t total = h_binom[n - (7 - P)][P];
+  const uint64_t tickets = (total + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
 #define SBG_LAUNCH_PM(NWV, WV)                                                                 \
   {                                                                                            \
-    const size_t smem = filter_pm_smem<NWV>(n, m);                                             \
-    int grid = grid_for(h, k_filter7_pm<NWV, WV>, smem, tickets);                              \
+    const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
+    int grid = grid_for(h, k_filter7_pm<NWV, WV, P>, smem, tickets);                           \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(tickets, n, 4);                                                  \
+    uint64_t bsz = pick_batch(tickets, n, P == 4 ? 4 : 6);                                     \
     if (max_warps > 0) bsz = 1;                                                                \
-    k_filter7_pm<NWV, WV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_hits, \
-        cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);             \
+    k_filter7_pm<NWV, WV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,         \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
   }
   if (n <= 32) {  // one word of candidate gates per pass
     switch (h->nw) {
@@ -335,6 +342,13 @@ int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
   h->launches++;
   SBG_CUDA(h, cudaGetLastError());
   return SBG_OK;
+}
+
+int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
+  static const char *env = getenv("SBG_PM_PREFIX");
+  const bool five = env != nullptr ? atoi(env) == 5 : h->n >= kPm5MinGates;
+  return five ? launch_filter7_pm_p<5>(h, part, nparts, max_warps)
+              : launch_filter7_pm_p<4>(h, part, nparts, max_warps);
 }
 
 // Which phase-1 kernel: the position-major one unless SBG_FILTER=sweep asks for the bitmap sweep.

@@ -497,11 +497,14 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 // usually empties after the first cell.  Cost per lane: ~30 instructions per visited position for
 // up to 64 candidate g, against ~100 per (pair, cell) in k_sweep.
 // W = 32-bit words of candidate gates handled per pass: 1 when n <= 32, else 2.
-template <int NW, int W>
+// P = gates in the prefix a warp owns: 4 (lanes take (e,f) pairs, four parts per cell) or 5 (lanes
+// take single gates f, two parts per cell: half the masked-accumulate work per position and half
+// the positions per cell, at the price of fewer busy lanes -- it wins once n - 7 approaches a warp).
+template <int NW, int W, int P>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
     int nparts, unsigned long long list_cap, int batch, int max_warps) {
-  constexpr int P = 4, K = 7, NC = 16;
+  constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
   const int n = prob->n;
   const int m = prob->m;
@@ -527,7 +530,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     M[w] = prob->M[w];
   }
   const uint32_t inmask = prob->inmask;
-  const uint64_t total = c_binom[n - 3][P];
+  const uint64_t total = c_binom[n - (K - P)][P];
   unsigned long long swept_local = 0;
   unsigned long long next_b = 0;
   auto fetch = [&]() {
@@ -556,20 +559,20 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     for (uint64_t gt = t_first; gt < t_end; gt++) {
       if (gt != t_first) {
         int i = P - 1;
-        while (i > 0 && pre[i] + (P - i) >= n - 3) i--;
+        while (i > 0 && pre[i] + (P - i) >= n - (K - P)) i--;
         pre[i]++;
         for (int k2 = i + 1; k2 < P; k2++) pre[k2] = pre[k2 - 1] + 1;
       }
       const int last = pre[P - 1];
-      const int r = n - last - 2;                   // candidates for e,f: last+1 .. n-2
-      const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
-      swept_local += c_binom[n - last - 1][3];      // 7-combinations sharing this prefix
+      const int r = n - last - 2;                   // candidates for (e,)f: last+1 .. n-2
+      const uint32_t Q = P == 4 ? (uint32_t)(r * (r - 1) / 2) : (uint32_t)r;
+      swept_local += c_binom[n - last - 1][K - P];  // 7-combinations sharing this prefix
       bool rejected = false;
 #pragma unroll
       for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
       if (rejected) continue;
 
-      // mixed cells of the prefix (lane < 16 = cell, first gate most significant)
+      // mixed cells of the prefix (lane < NC = cell, first gate most significant)
       uint32_t mixed_ballot;
       {
         uint32_t c[NW];
@@ -603,19 +606,24 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
       for (uint32_t q0 = 0; q0 < Q && !prefix_done; q0 += 32) {
         const uint32_t q = q0 + lane;
         bool lane_ok = q < Q;
-        int pi, pj;
-        unrank_pair(lane_ok ? q : 0u, r, pi, pj);
-        const int ge = last + 1 + pi;
+        int pi = 0, pj = 0;
+        if (P == 4) {
+          unrank_pair(lane_ok ? q : 0u, r, pi, pj);
+        } else {
+          pj = lane_ok ? (int)q : 0;
+        }
+        const int ge = P == 4 ? last + 1 + pi : pre[P - 1];   // P == 5: e is the prefix's last gate
         const int gf = last + 1 + pj;
-        if ((ge < 8 && ((inmask >> ge) & 1u)) || (gf < 8 && ((inmask >> gf) & 1u))) lane_ok = false;
+        if (P == 4 && ge < 8 && ((inmask >> ge) & 1u)) lane_ok = false;
+        if (gf < 8 && ((inmask >> gf) & 1u)) lane_ok = false;
         uint32_t te[NW], tf[NW];
 #pragma unroll
         for (int w = 0; w < NW; w++) {
           te[w] = s_tabs[w * npad + ge];
           tf[w] = s_tabs[w * npad + gf];
         }
-        // windows of 64 candidate gates g; the first window that can hold a g > last + 2
-        for (int wb = ((last + 3) >> 5) & ~(W - 1); wb < ((n + 31) >> 5); wb += W) {
+        // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
+        for (int wb = ((last + (K - P)) >> 5) & ~(W - 1); wb < ((n + 31) >> 5); wb += W) {
           uint32_t V[W];
 #pragma unroll
           for (int j = 0; j < W; j++) {
@@ -632,9 +640,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
           for (int j = 0; j < W; j++) alive |= V[j] != 0;
           for (int cj = 0; cj < mc; cj++) {
             if (!__any_sync(kFull, alive)) break;
-            uint32_t a_and[4][W], a_or[4][W];
+            uint32_t a_and[NP][W], a_or[NP][W];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < NP; k++) {
 #pragma unroll
               for (int j = 0; j < W; j++) {
                 a_and[k][j] = 0xffffffffu;
@@ -650,7 +658,11 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 bits &= bits - 1;
                 const int p = w * 32 + j;
                 const uint32_t tp = (T[w] >> j) & 1u;
-                const uint32_t pk = (((te[w] >> j) & 1u) << 1) | ((tf[w] >> j) & 1u);
+                // eb / fb = bit j of the lane's e / f table spread over a whole word (shift it to
+                // the sign position, arithmetic shift back): all-ones / zero masks without a
+                // predicate, so that every masked accumulate below is ONE three-input LOP3.
+                const uint32_t fb = (uint32_t)((int32_t)(tf[w] << (31 - j)) >> 31);
+                const uint32_t eb = P == 4 ? (uint32_t)((int32_t)(te[w] << (31 - j)) >> 31) : 0u;
                 uint32_t x[W];
                 if (W == 2) {
                   const uint2 xx = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
@@ -659,21 +671,30 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 } else {
                   x[0] = s_xr[p * ngw + wb];
                 }
-                if (tp) has1 |= 1u << pk; else has0 |= 1u << pk;
+                uint32_t mk[NP];   // mk[k] = all-ones iff this position lies in part k
+                if (P == 4) {
+                  mk[0] = ~(eb | fb);
+                  mk[1] = ~eb & fb;
+                  mk[NP - 2] = eb & ~fb;
+                  mk[NP - 1] = eb & fb;
+                } else {
+                  mk[0] = ~fb;
+                  mk[NP - 1] = fb;
+                }
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                  const uint32_t mk = (pk == (uint32_t)k) ? 0xffffffffu : 0u;
+                for (int k = 0; k < NP; k++) {
+                  if (tp) has1 |= mk[k] & (1u << k); else has0 |= mk[k] & (1u << k);
 #pragma unroll
                   for (int jw = 0; jw < W; jw++) {
-                    a_and[k][jw] &= x[jw] | ~mk;
-                    a_or[k][jw] |= x[jw] & mk;
+                    a_and[k][jw] &= x[jw] | ~mk[k];
+                    a_or[k][jw] |= x[jw] & mk[k];
                   }
                 }
               }
             }
             const uint32_t both = has1 & has0;
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < NP; k++) {
               if ((both >> k) & 1u) {
 #pragma unroll
                 for (int jw = 0; jw < W; jw++) V[jw] &= a_and[k][jw] | ~a_or[k][jw];
@@ -701,7 +722,11 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
           uint64_t head = 0;
 #pragma unroll
           for (int i = 0; i < P; i++) head = (head << 9) | (uint64_t)pre[i];
-          head = (head << 27) | ((uint64_t)ge << 18) | ((uint64_t)gf << 9);
+          if (P == 4) {
+            head = (head << 27) | ((uint64_t)ge << 18) | ((uint64_t)gf << 9);
+          } else {
+            head = (head << 18) | ((uint64_t)gf << 9);
+          }
 #pragma unroll
           for (int j = 0; j < W; j++) {
             uint32_t v = V[j];
