@@ -451,7 +451,7 @@ def main():
                     "note": "host tables -> sbg_load_problem -> sbg_search5/7 -> result structs"},
             "gpu_launches": acc_res["launches"],
             "roofline": {
-                "bound": "hbm", "kernel": "k_filter7_pm<NW> (search_7lut phase 1)",
+                "bound": "hbm", "kernel": "k_filter7_pm<NW,W,P> (search_7lut phase 1)",
                 "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "traffic": dram_per_launch,
