@@ -275,6 +275,10 @@ def main():
     ap.add_argument("--gates", type=int, default=40)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="auto", choices=["auto", "states", "tuples"],
+                    help="N > 1: deal the step's independent search states to the ranks (states), or "
+                         "shard every search over the tuple space (tuples); auto = states when the "
+                         "batch has at least N states")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -284,7 +288,12 @@ def main():
                           "S-box bit 0, mux masks of depth 0-3, full no-match sweeps of "
                           "search_5lut+search_7lut" % (args.batch, args.gates),
               "gates": args.gates, "states_per_step": args.batch,
-              "parallelism": "tuple-space sharded over %d GPU(s)" % world,
+              "parallelism": "1 GPU" if world == 1 else (
+                  "%d ranks; the step's independent search states are dealt round-robin to the ranks "
+                  "(one all-gather of the result keys per step)" % world if
+                  (args.shard == "states" or (args.shard == "auto" and args.batch >= world)) else
+                  "%d ranks; every search sharded over the tuple space (all-gather of hit lists + "
+                  "all-reduce(MIN) per phase above the size thresholds, replicated below)" % world),
               "l2": "a 256 MiB buffer is overwritten between steps (L2 flush); every step uses new states"}
 
     if args.impl == "reference":
@@ -317,7 +326,8 @@ def main():
     eng = sb.LutEngine(local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    drv = DistributedLutSearch(eng) if world > 1 else None
+    by_states = world > 1 and (args.shard == "states" or (args.shard == "auto" and args.batch >= world))
+    drv = DistributedLutSearch(eng) if world > 1 and not by_states else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -333,7 +343,10 @@ def main():
     def run_step(states, resident, acc):
         """One step.  resident=True: states are already staged in HBM slots (value);
         False: host tables go through sbg_load_problem inside the step (e2e)."""
+        keys = []
         for i, st in enumerate(states):
+            if by_states and i % world != rank:
+                continue          # another rank's state
             if resident:
                 eng.use(i)
             else:
@@ -346,6 +359,7 @@ def main():
                 r5 = drv.search5_sharded(st["order5"])
                 k5 = eng.kernel_ms(0)
                 r7 = drv.search7_sharded(st["outer"], st["middle"])
+            keys += [int(r5.key) & 0x7FFFFFFFFFFFFFFF, int(r7.key) & 0x7FFFFFFFFFFFFFFF]
             if acc is not None:
                 t5, t7, c = units_of(n, r5, r7)
                 acc["T"] += t5
@@ -358,6 +372,13 @@ def main():
                 acc["ms_filter"] += eng.kernel_ms(1)
                 acc["ms_sort"] += eng.kernel_ms(2)
                 acc["ms_decomp"] += eng.kernel_ms(3)
+        if by_states:
+            # every rank ends the step knowing every state's result, as the host program would
+            per = 2 * ((len(states) + world - 1) // world)
+            mine = torch.full((per,), -1, dtype=torch.int64, device="cuda")
+            mine[:len(keys)] = torch.tensor(keys, dtype=torch.int64)
+            allk = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allk, mine)
 
     def timed(resident):
         acc = {"T": 0, "C": 0, "T7": 0, "T7_rep": 0, "ms5": 0.0, "ms_filter": 0.0, "ms_sort": 0.0,
@@ -367,7 +388,8 @@ def main():
         for s in range(args.warmup):
             if resident:
                 for i, st in enumerate(batches[s]):
-                    eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
+                    if not by_states or i % world == rank:
+                        eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
             run_step(batches[s], resident, None)
         launches0 = eng.launches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -378,7 +400,8 @@ def main():
             states = batches[args.warmup + s]
             if resident:   # inputs resident in HBM before the timed region of this step starts
                 for i, st in enumerate(states):
-                    eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
+                    if not by_states or i % world == rank:
+                        eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
             flush.fill_(s & 0xFF)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -397,10 +420,13 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        if world > 1:   # phase-1 tuples are swept by different ranks: sum the shares
-            t = torch.tensor([acc["T7"]], dtype=torch.int64, device="cuda")
+        if world > 1:   # units are produced on different ranks: sum the shares
+            t = torch.tensor([acc["T7"]] + ([acc["T"], acc["C"]] if by_states else [0, 0]),
+                             dtype=torch.int64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            acc["T7"] = int(t.item())
+            acc["T7"] = int(t[0].item())
+            if by_states:
+                acc["T"], acc["C"] = int(t[1].item()), int(t[2].item())
             t = torch.tensor([acc["ms_filter"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             acc["ms_filter"] = float(t.item())

@@ -12,6 +12,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
+#include <utility>
 
 #include "../../include/sboxgates_b200.h"
 
@@ -226,8 +228,18 @@ size_t decomp_smem(int n) {
 // Persistent grid: as many CTAs as are resident at once, but no more than there is work for.
 template <typename Kernel>
 int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_warps) {
+  // the occupancy query costs a few microseconds; a search makes several launches and a graph
+  // build makes tens of thousands of searches, so remember the answer per (kernel, smem size)
+  static std::map<std::pair<const void *, size_t>, int> cache;
+  const auto key = std::make_pair(reinterpret_cast<const void *>(kernel), smem);
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    per_sm = it->second;
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem);
+    cache[key] = per_sm;
+  }
   if (per_sm < 1) per_sm = 1;
   uint64_t want = (work_items_in_warps + kWarpsPerCta - 1) / kWarpsPerCta;
   uint64_t cap = (uint64_t)per_sm * (uint64_t)h->sm_count;
