@@ -180,6 +180,7 @@ struct sbg_handle {
 
   uint64_t swept = 0;
   uint64_t feasible = 0;
+  std::map<std::pair<const void *, size_t>, int> occupancy;  // grid_for's cache
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
   float ms[4] = {0, 0, 0, 0};
@@ -230,7 +231,7 @@ template <typename Kernel>
 int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_warps) {
   // the occupancy query costs a few microseconds; a search makes several launches and a graph
   // build makes tens of thousands of searches, so remember the answer per (kernel, smem size)
-  static std::map<std::pair<const void *, size_t>, int> cache;
+  auto &cache = h->occupancy;   // per handle: handles may be driven from different threads
   const auto key = std::make_pair(reinterpret_cast<const void *>(kernel), smem);
   int per_sm = 1;
   auto it = cache.find(key);

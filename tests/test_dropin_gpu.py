@@ -51,3 +51,32 @@ def test_dropin_finishes_rijndael_single_output():
     assert len(got) == 1 and got[0].startswith("1-0")
     assert got[0] == "1-031-0000-0-55aa04f1.xml"   # stable across every kernel rewrite of round 1
     assert secs < 120
+
+
+@pytest.mark.skipif(not os.path.exists(EXE), reason="oracle/_ref/sboxgates_gpu not built")
+def test_dropin_sharded_over_two_devices_gives_the_same_graph():
+    """SBG_GPUS=2 with the sharding thresholds at zero: every search is split over two devices
+    (one host thread each); the graph must not change.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    names = json.load(open(os.path.join(S.GOLDEN, "xml_names.json")))
+    key = "des_s1.txt -l -o 0 seed1"
+    env_extra = {"SBG_GPUS": "2", "SBG_SHARD_MIN5": "0", "SBG_SHARD_MIN7": "0",
+                 "SBG_SHARD_MIN_LIST": "0"}
+    old = {k: os.environ.get(k) for k in env_extra}
+    os.environ.update(env_extra)
+    try:
+        with tempfile.TemporaryDirectory() as tmp:
+            got, secs, err = _run("des_s1.txt", ["-l", "-o", "0"], "seed1", tmp)
+        assert got == names[key]
+        assert "sharded search phases" in err
+        with tempfile.TemporaryDirectory() as tmp:
+            got, secs, err = _run("rijndael.txt", ["-l", "-o", "0"], "seed1", tmp)
+        assert got == ["1-031-0000-0-55aa04f1.xml"]
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
