@@ -181,6 +181,12 @@ struct sbg_handle {
   uint64_t swept = 0;
   uint64_t feasible = 0;
   std::map<std::pair<const void *, size_t>, int> occupancy;  // grid_for's cache
+  // tuning knobs, read from the environment when the handle is created (tests create handles under
+  // different settings to cross-check the alternative kernels against each other)
+  int opt_batch = 0;        // SBG_BATCH: prefixes per ticket batch (0 = automatic)
+  int opt_pm_prefix = 0;    // SBG_PM_PREFIX: 4 or 5 (0 = by n)
+  int opt_filter = 0;       // SBG_FILTER: 0 position-major, 1 bitmap sweep
+  int opt_search5 = 0;      // SBG_SEARCH5: 0 by size, 1 fused, 2 two kernels
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
   float ms[4] = {0, 0, 0, 0};
@@ -257,11 +263,10 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
 // problem and a nominal warp count only, never of the device a rank happens to run on.
 constexpr uint64_t kNominalWarps = 148 * 2 * kWarpsPerCta;
 
-uint64_t pick_batch(uint64_t tickets, int n, int P) {
+uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   const uint64_t warps = kNominalWarps;
-  static const char *env = getenv("SBG_BATCH");
-  if (env != nullptr) {
-    uint64_t b = std::max<uint64_t>(1, std::min<uint64_t>(16, strtoull(env, nullptr, 10)));
+  if (h->opt_batch > 0) {
+    uint64_t b = std::max<uint64_t>(1, std::min<uint64_t>(16, (uint64_t)h->opt_batch));
     while (b & (b - 1)) b &= b - 1;
     return b;
   }
@@ -289,7 +294,7 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
     const size_t smem = sweep_smem<NWV, P>(n);                                                 \
     int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(tickets, n, P);                                                  \
+    uint64_t bsz = pick_batch(h, tickets, n, P);                                                  \
     if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
@@ -331,7 +336,7 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
     const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
     int grid = grid_for(h, k_filter7_pm<NWV, WV, P>, smem, tickets);                           \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(tickets, n, P == 4 ? 4 : 6);                                     \
+    uint64_t bsz = pick_batch(h, tickets, n, P == 4 ? 4 : 6);                                     \
     if (max_warps > 0) bsz = 1;                                                                \
     k_filter7_pm<NWV, WV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,         \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
@@ -358,18 +363,14 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
 }
 
 int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
-  static const char *env = getenv("SBG_PM_PREFIX");
-  const bool five = env != nullptr ? atoi(env) == 5 : h->n >= kPm5MinGates;
+  const bool five = h->opt_pm_prefix != 0 ? h->opt_pm_prefix == 5 : h->n >= kPm5MinGates;
   return five ? launch_filter7_pm_p<5>(h, part, nparts, max_warps)
               : launch_filter7_pm_p<4>(h, part, nparts, max_warps);
 }
 
 // Which phase-1 kernel: the position-major one unless SBG_FILTER=sweep asks for the bitmap sweep.
 bool use_position_major(const sbg_handle *h) {
-  static const char *env = getenv("SBG_FILTER");
-  if (env != nullptr) return strcmp(env, "sweep") != 0;
-  (void)h;
-  return true;
+  return h->opt_filter == 0;
 }
 
 // count_on_device: the list length is ctl->list_count (written by k_sort_small); the grid is then
@@ -537,9 +538,8 @@ int launch_decomp5(sbg_handle *h) {
 // ordered early exit matters there.  Either way one host synchronisation.
 int run_search5(sbg_handle *h, int part, int nparts, const uint8_t *func_order, uint64_t *key) {
   int rc;
-  static const char *mode_env = getenv("SBG_SEARCH5");
   const uint64_t two_kernel_max = 4000000;  // C(n,5) up to n = 52
-  bool two = mode_env != nullptr ? strcmp(mode_env, "two") == 0 : h_binom[h->n][5] <= two_kernel_max;
+  bool two = h->opt_search5 != 0 ? h->opt_search5 == 2 : h_binom[h->n][5] <= two_kernel_max;
   for (int pos = 0; pos < 256; pos++) h->h_pos5[func_order[pos]] = (uint8_t)pos;
   SBG_CUDA(h, cudaMemcpyAsync(h->d_pos5, h->h_pos5, 256, cudaMemcpyHostToDevice, h->stream));
   for (;;) {
@@ -746,6 +746,12 @@ int sbg_create(sbg_handle **out, int device) {
   SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
   SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
   stamp("small buffers + pinned");
+  if (getenv("SBG_BATCH") != nullptr) h->opt_batch = atoi(getenv("SBG_BATCH"));
+  if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
+  if (getenv("SBG_FILTER") != nullptr) h->opt_filter = strcmp(getenv("SBG_FILTER"), "sweep") == 0;
+  if (getenv("SBG_SEARCH5") != nullptr) {
+    h->opt_search5 = strcmp(getenv("SBG_SEARCH5"), "two") == 0 ? 2 : 1;
+  }
   const char *cap_env = getenv("SBG_HITS_CAP");
   h->hits_cap = cap_env != nullptr ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)32 << 20);
   if (h->hits_cap < 3 * kPerPrefixMax) h->hits_cap = 3 * kPerPrefixMax;
