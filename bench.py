@@ -160,7 +160,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -383,7 +383,7 @@ def main():
     def timed(resident):
         acc = {"T": 0, "C": 0, "T7": 0, "T7_rep": 0, "ms5": 0.0, "ms_filter": 0.0, "ms_sort": 0.0,
                "ms_decomp": 0.0}
-        sampler = ClockSampler(local_rank)   # samples every 100 ms from the warm-up on
+        sampler = ClockSampler(local_rank)   # samples every 20 ms from the warm-up on
         sampler.start()
         for s in range(args.warmup):
             if resident:
