@@ -322,7 +322,7 @@ size_t filter_pm_smem(int n, int m) {
 // Position-major phase 1 (k_filter7_pm): work items are 4- or 5-gate prefixes.  The 5-gate form does
 // half the work per visited position but keeps only n-7-ish lanes of a warp busy, so it is used
 // from n = kPm5MinGates on (measured cross-over, profiles/); SBG_PM_PREFIX=4|5 overrides.
-constexpr int kPm5MinGates = 64;
+constexpr int kPm5MinGates = 96;
 
 template <int P>
 int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {

@@ -649,7 +649,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 a_or[k][j] = 0u;
               }
             }
-            uint32_t has1 = 0, has0 = 0;
+            uint32_t seen1[NP], seen0[NP];
+#pragma unroll
+            for (int k = 0; k < NP; k++) seen1[k] = seen0[k] = 0u;
 #pragma unroll
             for (int w = 0; w < NW; w++) {
               uint32_t bits = cells[cj * NW + w];
@@ -681,9 +683,17 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                   mk[0] = ~fb;
                   mk[NP - 1] = fb;
                 }
+                // which targets each part has seen: whole-word flags, updated under a warp-uniform
+                // branch (tp belongs to the position, not to the lane)
+                if (tp) {
+#pragma unroll
+                  for (int k = 0; k < NP; k++) seen1[k] |= mk[k];
+                } else {
+#pragma unroll
+                  for (int k = 0; k < NP; k++) seen0[k] |= mk[k];
+                }
 #pragma unroll
                 for (int k = 0; k < NP; k++) {
-                  if (tp) has1 |= mk[k] & (1u << k); else has0 |= mk[k] & (1u << k);
 #pragma unroll
                   for (int jw = 0; jw < W; jw++) {
                     a_and[k][jw] &= x[jw] | ~mk[k];
@@ -692,13 +702,11 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 }
               }
             }
-            const uint32_t both = has1 & has0;
 #pragma unroll
             for (int k = 0; k < NP; k++) {
-              if ((both >> k) & 1u) {
+              const uint32_t both = seen1[k] & seen0[k];   // all-ones iff the part has both targets
 #pragma unroll
-                for (int jw = 0; jw < W; jw++) V[jw] &= a_and[k][jw] | ~a_or[k][jw];
-              }
+              for (int jw = 0; jw < W; jw++) V[jw] &= a_and[k][jw] | ~a_or[k][jw] | ~both;
             }
             alive = false;
 #pragma unroll
