@@ -322,7 +322,7 @@ size_t filter_pm_smem(int n, int m) {
 // Position-major phase 1 (k_filter7_pm): work items are 4- or 5-gate prefixes.  The 5-gate form does
 // half the work per visited position but keeps only n-7-ish lanes of a warp busy, so it is used
 // from n = kPm5MinGates on (measured cross-over, profiles/); SBG_PM_PREFIX=4|5 overrides.
-constexpr int kPm5MinGates = 96;
+constexpr int kPm5MinGates = 128;
 
 template <int P>
 int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
@@ -331,29 +331,36 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
   const uint64_t total = h_binom[n - (7 - P)][P];
   const uint64_t tickets = (total + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
-#define SBG_LAUNCH_PM(NWV, WV)                                                                 \
+#define SBG_LAUNCH_PM(NWV, WV, FSV)                                                            \
   {                                                                                            \
     const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
-    int grid = grid_for(h, k_filter7_pm<NWV, WV, P>, smem, tickets);                           \
+    int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets);                      \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
     uint64_t bsz = pick_batch(h, tickets, n, P == 4 ? 4 : 6);                                     \
     if (max_warps > 0) bsz = 1;                                                                \
-    k_filter7_pm<NWV, WV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,         \
+    k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,    \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
   }
-  if (n <= 32) {  // one word of candidate gates per pass
+  if (n <= 31) {         // one word of candidate gates per pass, its top bit free
     switch (h->nw) {
-      case 1: SBG_LAUNCH_PM(1, 1) break;
-      case 2: SBG_LAUNCH_PM(2, 1) break;
-      case 4: SBG_LAUNCH_PM(4, 1) break;
-      default: SBG_LAUNCH_PM(8, 1) break;
+      case 1: SBG_LAUNCH_PM(1, 1, true) break;
+      case 2: SBG_LAUNCH_PM(2, 1, true) break;
+      case 4: SBG_LAUNCH_PM(4, 1, true) break;
+      default: SBG_LAUNCH_PM(8, 1, true) break;
+    }
+  } else if (n <= 63) {  // two words, one pass, top bit free
+    switch (h->nw) {
+      case 1: SBG_LAUNCH_PM(1, 2, true) break;
+      case 2: SBG_LAUNCH_PM(2, 2, true) break;
+      case 4: SBG_LAUNCH_PM(4, 2, true) break;
+      default: SBG_LAUNCH_PM(8, 2, true) break;
     }
   } else {
     switch (h->nw) {
-      case 1: SBG_LAUNCH_PM(1, 2) break;
-      case 2: SBG_LAUNCH_PM(2, 2) break;
-      case 4: SBG_LAUNCH_PM(4, 2) break;
-      default: SBG_LAUNCH_PM(8, 2) break;
+      case 1: SBG_LAUNCH_PM(1, 2, false) break;
+      case 2: SBG_LAUNCH_PM(2, 2, false) break;
+      case 4: SBG_LAUNCH_PM(4, 2, false) break;
+      default: SBG_LAUNCH_PM(8, 2, false) break;
     }
   }
 #undef SBG_LAUNCH_PM
@@ -886,9 +893,17 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
       }
     }
   }
+  // "free seen" (k_filter7_pm<.., FS = true>): with n <= 31 / n <= 63 the top bit of word 0 / 1 is
+  // no gate; it carries the position's target bit
+  const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
   for (int pos = 0; pos < m; pos++) {
-    if (!((p->T[pos >> 5] >> (pos & 31)) & 1u)) {
+    const bool t1 = ((p->T[pos >> 5] >> (pos & 31)) & 1u) != 0;
+    if (!t1) {
       for (int w = 0; w < 16; w++) p->xr[pos][w] = ~p->xr[pos][w];
+    }
+    if (spare >= 0) {
+      uint32_t &word = p->xr[pos][spare >> 5];
+      word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
     }
   }
   SBG_CUDA(h, cudaMemcpyAsync(h->d_slots + slot, p, sizeof(DevProblem), cudaMemcpyHostToDevice,

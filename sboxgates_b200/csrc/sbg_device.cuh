@@ -76,6 +76,15 @@ __constant__ uint8_t c_j_first_k[25];    // first ordering row of outer triple j
 __constant__ uint8_t c_j_rows[25];       // rows sharing that outer triple (4 or 1)
 __constant__ uint8_t c_row_b[70];        // bit of v4 that is the g input in ordering row k
 
+// One LOP3 with the given truth table (inputs a = 0xF0, b = 0xCC, c = 0xAA), opaque to the
+// compiler so that it keeps the operand grouping chosen here.
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -500,7 +509,11 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 // P = gates in the prefix a warp owns: 4 (lanes take (e,f) pairs, four parts per cell) or 5 (lanes
 // take single gates f, two parts per cell: half the masked-accumulate work per position and half
 // the positions per cell, at the price of fewer busy lanes -- it wins once n - 7 approaches a warp).
-template <int NW, int W, int P>
+// FS ("free seen"): when all candidate gates fit one pass and leave the top bit of the last word
+// unused (n <= 31 with W = 1, n <= 63 with W = 2), the host stores the position's target bit there;
+// the AND / OR accumulators then also tell which targets a part has seen (OR = some 1, AND = only 1s)
+// and the separate bookkeeping disappears from the inner loop.
+template <int NW, int W, int P, bool FS>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
     int nparts, unsigned long long list_cap, int batch, int max_warps) {
@@ -674,37 +687,42 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                   x[0] = s_xr[p * ngw + wb];
                 }
                 uint32_t mk[NP];   // mk[k] = all-ones iff this position lies in part k
-                if (P == 4) {
-                  mk[0] = ~(eb | fb);
-                  mk[1] = ~eb & fb;
-                  mk[NP - 2] = eb & ~fb;
-                  mk[NP - 1] = eb & fb;
+                if (P == 4) {   // materialised, so that each accumulate below stays one LOP3
+                  mk[0] = lop3<0x03>(eb, fb, 0u);        // ~(eb | fb)
+                  mk[1] = lop3<0x0c>(eb, fb, 0u);        // ~eb & fb
+                  mk[NP - 2] = lop3<0x30>(eb, fb, 0u);   // eb & ~fb
+                  mk[NP - 1] = lop3<0xc0>(eb, fb, 0u);   // eb & fb
                 } else {
                   mk[0] = ~fb;
                   mk[NP - 1] = fb;
                 }
                 // which targets each part has seen: whole-word flags, updated under a warp-uniform
                 // branch (tp belongs to the position, not to the lane)
-                if (tp) {
+                if (!FS) {
+                  if (tp) {
 #pragma unroll
-                  for (int k = 0; k < NP; k++) seen1[k] |= mk[k];
-                } else {
+                    for (int k = 0; k < NP; k++) seen1[k] |= mk[k];
+                  } else {
 #pragma unroll
-                  for (int k = 0; k < NP; k++) seen0[k] |= mk[k];
+                    for (int k = 0; k < NP; k++) seen0[k] |= mk[k];
+                  }
                 }
 #pragma unroll
                 for (int k = 0; k < NP; k++) {
 #pragma unroll
                   for (int jw = 0; jw < W; jw++) {
-                    a_and[k][jw] &= x[jw] | ~mk[k];
-                    a_or[k][jw] |= x[jw] & mk[k];
+                    a_and[k][jw] = lop3<0xd0>(a_and[k][jw], x[jw], mk[k]);   // a & (x | ~m)
+                    a_or[k][jw] = lop3<0xf8>(a_or[k][jw], x[jw], mk[k]);     // a | (x & m)
                   }
                 }
               }
             }
 #pragma unroll
             for (int k = 0; k < NP; k++) {
-              const uint32_t both = seen1[k] & seen0[k];   // all-ones iff the part has both targets
+              // all-ones iff the part has both targets
+              const uint32_t both = FS
+                  ? (uint32_t)((int32_t)(a_or[k][W - 1] & ~a_and[k][W - 1]) >> 31)
+                  : (seen1[k] & seen0[k]);
 #pragma unroll
               for (int jw = 0; jw < W; jw++) V[jw] &= a_and[k][jw] | ~a_or[k][jw] | ~both;
             }
