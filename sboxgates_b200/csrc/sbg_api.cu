@@ -148,6 +148,7 @@ struct sbg_handle {
   DevParams7 *h_par7 = nullptr;  // = &h_call->par
   DevCtl *h_ctl_out = nullptr;   // pinned: control words read back
   uint64_t *h_head = nullptr;    // pinned: first kHeadEntries of the sorted list, read back with them
+  DevTables *d_tab = nullptr;    // lane-indexed ordering tables
   uint8_t *d_pos5 = nullptr;
   uint8_t *h_pos5 = nullptr;     // pinned
 
@@ -298,7 +299,7 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
     if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
-        emit5);                                                                                \
+        emit5, h->d_tab);                                                                      \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_SWEEP(1) break;
@@ -392,7 +393,7 @@ int launch_decomp7(sbg_handle *h, int part, int nparts, bool count_on_device = f
     const size_t smem = decomp_smem<NWV>(n);                                                   \
     const int grid = grid_for(h, k_decomp7<NWV>, smem, items);                                 \
     k_decomp7<NWV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_par7,        \
-        h->d_list, count_arg, part, nparts);                                                   \
+        h->d_list, count_arg, part, nparts, h->d_tab);                                         \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_DECOMP(1) break;
@@ -525,7 +526,7 @@ int launch_decomp5(sbg_handle *h) {
   {                                                                                            \
     const size_t smem = decomp_smem<NWV>(n);                                                   \
     k_decomp5<NWV><<<2 * h->sm_count, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,        \
-        h->d_pos5, h->d_hits);                                                                 \
+        h->d_pos5, h->d_hits, h->d_tab);                                                       \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_D5(1) break;
@@ -687,7 +688,8 @@ int sbg_create(sbg_handle **out, int device) {
         src5[k][lane] = (uint8_t)c;
       }
     }
-    SBG_CUDA(h, cudaMemcpyToSymbol(c_src5, src5, sizeof(src5)));
+    DevTables host_tab;
+    memcpy(host_tab.src5, src5, sizeof(src5));
 
     // decomp7: group the 70 rows by outer triple; canonical cell bit of slot s (tuple_summary):
     // a..e -> 4..0, f -> 6, g -> 5.
@@ -731,7 +733,9 @@ int sbg_create(sbg_handle **out, int device) {
       k += rows;
     }
     if (nj != 25) return fail(h, SBG_ERR_STATE, "internal: %d outer triples (expected 25)", nj);
-    SBG_CUDA(h, cudaMemcpyToSymbol(c_src7, src7, sizeof(src7)));
+    memcpy(host_tab.src7, src7, sizeof(src7));
+    SBG_CUDA(h, cudaMalloc(&h->d_tab, sizeof(DevTables)));
+    SBG_CUDA(h, cudaMemcpy(h->d_tab, &host_tab, sizeof(DevTables), cudaMemcpyHostToDevice));
     SBG_CUDA(h, cudaMemcpyToSymbol(c_j_first_k, first_k, sizeof(first_k)));
     SBG_CUDA(h, cudaMemcpyToSymbol(c_j_rows, nrows, sizeof(nrows)));
     SBG_CUDA(h, cudaMemcpyToSymbol(c_row_b, row_b, sizeof(row_b)));
@@ -782,6 +786,7 @@ void sbg_destroy(sbg_handle *h) {
     cudaFree(h->d_call); cudaFreeHost(h->h_call);
     cudaFreeHost(h->h_ctl_out); cudaFreeHost(h->h_head);
     cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
+    cudaFree(h->d_tab);
     cudaFree(h->d_hits); cudaFree(h->d_sorted); cudaFree(h->d_cub);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->own_stream);

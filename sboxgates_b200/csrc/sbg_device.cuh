@@ -69,9 +69,14 @@ struct DevParams7 {
   uint8_t minpos3[kMinpos3 + 3];   // device-built; not part of the upload
 };
 
+// Lane-indexed lookup tables live in global memory (coalesced, L1-resident): a constant-memory load
+// whose address differs per lane is replayed once per distinct address.
+struct DevTables {
+  uint8_t src5[10][32];    // search5: ordering k, lane (u,v2) -> canonical cell
+  uint32_t src7[25][32];   // decomp7: outer triple j, lane (u0,v4) -> 4 cells (u2,u1)
+};
+
 __constant__ uint64_t c_binom[501][8];   // C(m, r), 0 <= m <= 500, 0 <= r <= 7
-__constant__ uint8_t c_src5[10][32];     // search5: ordering k, lane (u,v2) -> canonical cell
-__constant__ uint32_t c_src7[25][32];    // decomp7: outer triple j, lane (u0,v4) -> 4 cells (u2,u1)
 __constant__ uint8_t c_j_first_k[25];    // first ordering row of outer triple j
 __constant__ uint8_t c_j_rows[25];       // rows sharing that outer triple (4 or 1)
 __constant__ uint8_t c_row_b[70];        // bit of v4 that is the g input in ordering row k
@@ -145,9 +150,11 @@ __device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
 // 256 outer functions decided from the tuple's 32-cell summary H1/H0 (cells that contain a masked
 // 1 / a masked 0 of the target).  Returns the first (ordering, position in the shuffled function
 // order) that decomposes, as k<<8 | pos, or 0xffffffff.
+
 template <int NW>
 __device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int npad, const int *g,
-    const uint32_t *T, const uint32_t *M, int lane, const uint8_t *s_pos) {
+    const uint32_t *T, const uint32_t *M, int lane, const uint8_t *s_pos,
+    const DevTables *__restrict__ tab) {
   uint32_t ones = 0, zeros = 0;
 #pragma unroll
   for (int w = 0; w < NW; w++) {
@@ -163,7 +170,7 @@ __device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int np
   const uint32_t H1 = __ballot_sync(kFull, ones != 0);
   const uint32_t H0 = __ballot_sync(kFull, zeros != 0);
   for (int k = 0; k < 10; k++) {
-    const int s = c_src5[k][lane];
+    const int s = tab->src5[k][lane];
     const uint32_t b1 = __ballot_sync(kFull, (H1 >> s) & 1u);
     const uint32_t b0 = __ballot_sync(kFull, (H0 >> s) & 1u);
     // wv(u): bits 0-3 = inner cells (x, d, e) with a masked 1 contributed by outer pattern u,
@@ -214,7 +221,7 @@ template <int NW, int P>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
     unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
-    int batch, int max_warps, bool emit5) {
+    int batch, int max_warps, bool emit5, const DevTables *__restrict__ tab) {
   constexpr int K = P + 2;
   constexpr int NC = 1 << P;
   extern __shared__ uint32_t smem[];
@@ -435,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
           g5[3] = __shfl_sync(kFull, gf, src);
           g5[4] = __shfl_sync(kFull, gg, src);
           if (lane == 0) atomicAdd(&ctl->feasible, 1ull);
-          const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos);
+          const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
           if (hit != 0xffffffffu) {
             const uint64_t key = ((base_rank + q0 + src) << 12) | (uint64_t)hit;
             if (lane == 0) {
@@ -457,7 +464,8 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
 // Second kernel of the two-kernel search_5lut: one warp per recorded feasible 5-tuple.
 template <int NW>
 __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, const uint64_t *__restrict__ hits) {
+    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, const uint64_t *__restrict__ hits,
+    const DevTables *__restrict__ tab) {
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_pos[256];
   const unsigned long long count = ctl->hit_count;
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
     int g5[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) g5[i] = (int)((packed >> (9 * (4 - i))) & 0x1ffu);
-    const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos);
+    const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
     if (hit != 0xffffffffu && lane == 0) {
       atomicMin(&ctl->best, (unsigned long long)((rank << 12) | (uint64_t)hit));
     }
@@ -911,12 +919,13 @@ __device__ __forceinline__ void tuple_summary(const uint32_t *s_tabs, int npad, 
 template <int NW>
 __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const DevParams7 *__restrict__ par, const uint64_t *__restrict__ list,
-    unsigned int count, int part, int nparts) {
+    unsigned int count, int part, int nparts, const DevTables *__restrict__ tab) {
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_minpos[kMinpos3 + 3];
   __shared__ uint16_t s_p3[256];
   __shared__ uint8_t s_pos[256];
   __shared__ uint8_t s_fo[kWarpsPerCta][256];
+  __shared__ uint32_t s_src7[25 * 32];   // copy of DevTables::src7
   __shared__ uint32_t s_H[kWarpsPerCta][24];
 
   if (count == 0xffffffffu) {  // list produced on the device by k_sort_small
@@ -935,6 +944,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   const int warp = threadIdx.x >> 5;
 
   for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_minpos[i] = par->minpos3[i];
+  for (int i = threadIdx.x; i < 25 * 32; i += blockDim.x) s_src7[i] = tab->src7[i >> 5][i & 31];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     s_pos[i] = par->pos_outer[i];
     int p3 = 0, w3 = 1;
@@ -991,7 +1001,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
     uint64_t key = 0;
     for (int j = 0; j < 25 && !found; j++) {
       const uint32_t *Hs = (stale && j == 0) ? sH + 8 : sH;
-      const uint32_t srcw = c_src7[j][lane];
+      const uint32_t srcw = s_src7[j * 32 + lane];
       uint32_t P1[4], P0[4];
 #pragma unroll
       for (int t4 = 0; t4 < 4; t4++) {
