@@ -16,9 +16,13 @@ C-unit = one candidate decomposition decided, counted as the reference enumerate
 feasible 5-tuple, 70 x 65,536 per listed 7-tuple) even though the kernels decide many at once from
 a per-tuple summary.  value = (T + C) / s; both are also reported separately.
 
-N > 1 (torchrun, one rank per GPU): the SAME batch, every search sharded over the ranks' GPUs
-(work items dealt round-robin; one all-gather of the 7-LUT hit lists and one all-reduce(MIN) per
-search phase) -- strong scaling.
+N > 1 (torchrun, one rank per GPU): the search states of a step are independent (in the program
+they are the 16 mux branches of create_circuit, the 8 output bits of -o -1 and the -i iterations),
+so every rank takes `--batch` states of a step of N x `--batch` and the ranks exchange only the
+result keys (one all-gather per step) -- weak scaling.  `--shard tuples` instead keeps `--batch`
+states in total and shards every single search over the ranks' GPUs (work items dealt round-robin;
+one all-gather of the 7-LUT hit lists and one all-reduce(MIN) per search phase) -- strong scaling
+of one search, which only pays for searches far larger than n = 40.
 
 --impl reference times the reference's own object code (oracle/_ref/libsbgref.so, built from the
 unmodified sources; the oracle port if that is absent) on the host cores, one process per core, each
@@ -275,23 +279,25 @@ def main():
     ap.add_argument("--gates", type=int, default=40)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="auto", choices=["auto", "states", "tuples"],
-                    help="N > 1: deal the step's independent search states to the ranks (states), or "
-                         "shard every search over the tuple space (tuples); auto = states when the "
-                         "batch has at least N states")
+    ap.add_argument("--shard", default="states", choices=["states", "tuples"],
+                    help="N > 1: states = every rank searches --batch independent states per step "
+                         "(weak scaling); tuples = --batch states in total, every search sharded "
+                         "over the tuple space (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    by_states = world > 1 and args.shard == "states"
+    n_states = args.batch * world if by_states else args.batch
+    scaling = "weak" if by_states or world == 1 else "strong"
     config = {"workload": "rijndael.txt --lut -o 0 shaped: %d states/step, n=%d gates, target = "
                           "S-box bit 0, mux masks of depth 0-3, full no-match sweeps of "
-                          "search_5lut+search_7lut" % (args.batch, args.gates),
-              "gates": args.gates, "states_per_step": args.batch,
+                          "search_5lut+search_7lut" % (n_states, args.gates),
+              "gates": args.gates, "states_per_step": n_states, "states_per_gpu": args.batch,
               "parallelism": "1 GPU" if world == 1 else (
-                  "%d ranks; the step's independent search states are dealt round-robin to the ranks "
-                  "(one all-gather of the result keys per step)" % world if
-                  (args.shard == "states" or (args.shard == "auto" and args.batch >= world)) else
+                  "%d ranks x %d independent search states per step "
+                  "(one all-gather of the result keys per step)" % (world, args.batch) if by_states else
                   "%d ranks; every search sharded over the tuple space (all-gather of hit lists + "
                   "all-reduce(MIN) per phase above the size thresholds, replicated below)" % world),
               "l2": "a 256 MiB buffer is overwritten between steps (L2 flush); every step uses new states"}
@@ -306,7 +312,7 @@ def main():
         best = max(vals, key=lambda v: v["value"])
         line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT,
                 "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
-                "ms_per_step": 1e3 * best["seconds"], "higher_is_better": True, "scaling": "strong",
+                "ms_per_step": 1e3 * best["seconds"], "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "u32 bitwise", "data": "synthetic", "config": config,
                 "cpu_baseline": best,
                 "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -326,7 +332,6 @@ def main():
     eng = sb.LutEngine(local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    by_states = world > 1 and (args.shard == "states" or (args.shard == "auto" and args.batch >= world))
     drv = DistributedLutSearch(eng) if world > 1 and not by_states else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -336,7 +341,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    n, B = args.gates, args.batch
+    n, B = args.gates, n_states
     total_steps = args.warmup + args.steps
     batches = [build_batch(n, B, 1000 + s) for s in range(total_steps)]
 
@@ -345,10 +350,10 @@ def main():
         False: host tables go through sbg_load_problem inside the step (e2e)."""
         keys = []
         for i, st in enumerate(states):
-            if by_states and i % world != rank:
+            if by_states and i // args.batch != rank:
                 continue          # another rank's state
             if resident:
-                eng.use(i)
+                eng.use(i % args.batch)
             else:
                 eng.load(st["tables"], st["target"], st["mask"], st["inbits"])
             if drv is None:
@@ -388,8 +393,8 @@ def main():
         for s in range(args.warmup):
             if resident:
                 for i, st in enumerate(batches[s]):
-                    if not by_states or i % world == rank:
-                        eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
+                    if not by_states or i // args.batch == rank:
+                        eng.stage(i % args.batch, st["tables"], st["target"], st["mask"], st["inbits"])
             run_step(batches[s], resident, None)
         launches0 = eng.launches
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -400,8 +405,8 @@ def main():
             states = batches[args.warmup + s]
             if resident:   # inputs resident in HBM before the timed region of this step starts
                 for i, st in enumerate(states):
-                    if not by_states or i % world == rank:
-                        eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
+                    if not by_states or i // args.batch == rank:
+                        eng.stage(i % args.batch, st["tables"], st["target"], st["mask"], st["inbits"])
             flush.fill_(s & 0xFF)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -420,6 +425,7 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
+        acc["T7_local"], acc["ms_filter_local"] = acc["T7"] + acc["T7_rep"], acc["ms_filter"]
         if world > 1:   # units are produced on different ranks: sum the shares
             t = torch.tensor([acc["T7"]] + ([acc["T"], acc["C"]] if by_states else [0, 0]),
                              dtype=torch.int64, device="cuda")
@@ -448,8 +454,9 @@ def main():
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
         # dominant kernel: the 7-LUT phase-1 sweep, one launch per state per step
-        filt_s = acc_res["ms_filter"] * 1e-3
-        achieved = acc_res["T7"] * BYTES_T7 / max(filt_s, 1e-12) / 1e9
+        # (per GPU: this rank's launches and the combinations they swept)
+        filt_s = acc_res["ms_filter_local"] * 1e-3
+        achieved = acc_res["T7_local"] * BYTES_T7 / max(filt_s, 1e-12) / 1e9
         dram_per_launch = None
         try:
             dram_per_launch = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[
@@ -459,7 +466,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32 bitwise (LOP3)",
+            "scaling": scaling, "vs_baseline": None, "dtype": "u32 bitwise (LOP3)",
             "data": "synthetic", "config": config,
             "t_units_per_s": acc_res["T"] / (ms_res * 1e-3),
             "c_units_per_s": acc_res["C"] / (ms_res * 1e-3),
