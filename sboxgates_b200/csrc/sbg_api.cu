@@ -177,6 +177,7 @@ struct sbg_handle {
   uint64_t *mask = nullptr;
   int n = 0;
   int nw = 0;
+  uint32_t inmask = 0;
   bool problem_ready = false;
 
   uint64_t swept = 0;
@@ -188,6 +189,8 @@ struct sbg_handle {
   int opt_pm_prefix = 0;    // SBG_PM_PREFIX: 4 or 5 (0 = by n)
   int opt_filter = 0;       // SBG_FILTER: 0 position-major, 1 bitmap sweep
   int opt_search5 = 0;      // SBG_SEARCH5: 0 by size, 1 fused, 2 two kernels
+  int opt_head = -1;        // SBG_HEAD: chunked phase of the 7-LUT filter, 0 none, 1 first prefixes,
+                            // 2 everything (-1 = by n and mask size)
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
   float ms[4] = {0, 0, 0, 0};
@@ -324,23 +327,120 @@ size_t filter_pm_smem(int n, int m) {
 // half the work per visited position but keeps only n-7-ish lanes of a warp busy, so it is used
 // from n = kPm5MinGates on (measured cross-over, profiles/); SBG_PM_PREFIX=4|5 overrides.
 constexpr int kPm5MinGates = 128;
+// Chunked phase of phase 1 (see k_filter7_pm): a head of kHeadWaves waves of (prefix, chunk) items
+// in front of the prefix form.  A list that fills early -- small masks make most combinations
+// feasible -- then costs microseconds instead of the first wave of whole-prefix batches, which at
+// large n is enormous (measured before: n = 200 / 300 / 500 with 16-32 masked positions took 2.6 /
+// 20 / 258 s through the overflow retry, now 0.1-0.35 ms; profiles/r01_dense_cases.md).  Sweeping
+// EVERYTHING in chunk items is much slower where the sweep has to cover the space (n = 128, 64
+// positions: 3.8 s against 0.25 s), so that form is kept for the overflow retry.  Below
+// kHeadAlwaysMinGates the head is used for small masks only, below kHeadMinGates never (measured:
+// the rijndael -o 0 run and bench.py at n = 40 are indifferent to it).
+constexpr int kHeadAlwaysMinGates = 128;
+constexpr int kHeadMaxPositions = 64;
+constexpr int kHeadMinGates = 48;
+constexpr uint64_t kHeadWaves = 64;
+constexpr size_t kPerChunkMax = 32 * 512;   // hits one (prefix, chunk) item can emit
+
+struct ChunkPlan {
+  unsigned long long items = 0;     // (prefix, chunk) items of the chunked phase
+  int chunks = 0;                   // chunks per prefix
+  unsigned long long t_offset = 0;  // rank of the first prefix left to the prefix form
+  bool all = false;                 // the chunked phase covers everything
+};
 
 template <int P>
-int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
+ChunkPlan plan_chunks(const sbg_handle *h, int m, bool retry) {
+  ChunkPlan pl;
+  const int n = h->n;
+  const int na = n - __builtin_popcount(h->inmask & 0xffu);   // allowed gates
+  const uint64_t total_c = na >= 7 ? h_binom[na - (7 - P)][P] : 0;
+  int mode = h->opt_head;
+  if (mode < 0) {
+    mode = n >= kHeadAlwaysMinGates || (m <= kHeadMaxPositions && n >= kHeadMinGates) ? 1 : 0;
+  }
+  // overflow retry: one form for everything, so that the bound on the hits in flight is simple --
+  // chunk items where a prefix is large, whole prefixes otherwise
+  if (retry) mode = n >= kHeadAlwaysMinGates ? 2 : 0;
+  if (mode == 0 || total_c == 0) return pl;
+  const uint64_t qmax = P == 4 ? h_binom[n - 5][2] : (uint64_t)(n - 6);
+  pl.chunks = (int)std::max<uint64_t>(1, (qmax + 31) / 32);
+  uint64_t prefixes = total_c;
+  if (mode == 1) {
+    prefixes = std::min<uint64_t>(total_c,
+        std::max<uint64_t>(1, kHeadWaves * kNominalWarps / (uint64_t)pl.chunks));
+  }
+  pl.items = prefixes * (uint64_t)pl.chunks;
+  pl.all = prefixes == total_c;
+  if (!pl.all) {
+    // the first allowed prefix not covered: index `prefixes` among the P-subsets of the allowed
+    // gates, as gate numbers, ranked among the P-subsets of all gates
+    int c[P];
+    uint64_t t = prefixes;
+    const int np = na - (7 - P);
+    int x = 0;
+    for (int pos = 0; pos < P; pos++) {
+      for (;; x++) {
+        const uint64_t cnt = h_binom[np - x - 1][P - pos - 1];
+        if (t < cnt) break;
+        t -= cnt;
+      }
+      c[pos] = x++;
+    }
+    for (int i = 0; i < P; i++) {
+      int g = c[i];
+      for (int bit = 0; bit < 8; bit++) g += (((h->inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
+      c[i] = g;
+    }
+    const int nr = n - (7 - P);
+    uint64_t rank = 0;
+    int prev = -1;
+    for (int pos = 0; pos < P; pos++) {
+      for (int y = prev + 1; y < c[pos]; y++) rank += h_binom[nr - y - 1][P - pos - 1];
+      prev = c[pos];
+    }
+    pl.t_offset = rank;
+  }
+  return pl;
+}
+
+// retry: the hit buffer overflowed; run again with the number of working warps bounded so that it
+// cannot (tickets taken synchronously, see the kernel).
+template <int P>
+int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, bool retry) {
   const int n = h->n;
   const int m = popcount256(h->mask);
   const uint64_t total = h_binom[n - (7 - P)][P];
-  const uint64_t tickets = (total + nparts - 1) / nparts;
   const unsigned long long cap = h->hits_cap;
+  const ChunkPlan pl = plan_chunks<P>(h, m, retry);
+  // No item is handed out once the list cap is reached, so with w warps at work the buffer holds
+  // fewer than cap + w x (hits one item can emit) entries; a whole prefix stops by itself after
+  // cap + one chunk.
+  const int max_warps = !retry ? 0 : (int)std::max<size_t>(1, pl.all
+      ? (h->hits_cap - SBG_LIST_CAP) / kPerChunkMax : h->hits_cap / kPerPrefixMax - 1);
+  const uint64_t tickets = pl.all ? 0 : (total - pl.t_offset + nparts - 1) / nparts;
+  const uint64_t chunk_tickets = (pl.items + nparts - 1) / nparts;
 #define SBG_LAUNCH_PM(NWV, WV, FSV)                                                            \
   {                                                                                            \
     const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
-    int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets);                      \
-    if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(h, tickets, n, P == 4 ? 4 : 6);                                     \
-    if (max_warps > 0) bsz = 1;                                                                \
-    k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,    \
-        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps);  \
+    if (pl.items > 0) {                                                                        \
+      int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, chunk_tickets);              \
+      if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta); \
+      k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,  \
+          h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, 1, max_warps, 0ull,  \
+          pl.items, pl.chunks);                                                                \
+      h->launches++;                                                                           \
+    }                                                                                          \
+    if (!pl.all) {                                                                             \
+      int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets);                    \
+      if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta); \
+      uint64_t bsz = pick_batch(h, tickets, n, P == 4 ? 4 : 6);                                \
+      if (max_warps > 0) bsz = 1;                                                              \
+      k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,  \
+          h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps, \
+          pl.t_offset, 0ull, 0);                                                               \
+      h->launches++;                                                                           \
+    }                                                                                          \
   }
   if (n <= 31) {         // one word of candidate gates per pass, its top bit free
     switch (h->nw) {
@@ -365,15 +465,14 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, int max_warps) {
     }
   }
 #undef SBG_LAUNCH_PM
-  h->launches++;
   SBG_CUDA(h, cudaGetLastError());
   return SBG_OK;
 }
 
-int launch_filter7_pm(sbg_handle *h, int part, int nparts, int max_warps) {
+int launch_filter7_pm(sbg_handle *h, int part, int nparts, bool retry) {
   const bool five = h->opt_pm_prefix != 0 ? h->opt_pm_prefix == 5 : h->n >= kPm5MinGates;
-  return five ? launch_filter7_pm_p<5>(h, part, nparts, max_warps)
-              : launch_filter7_pm_p<4>(h, part, nparts, max_warps);
+  return five ? launch_filter7_pm_p<5>(h, part, nparts, retry)
+              : launch_filter7_pm_p<4>(h, part, nparts, retry);
 }
 
 // Which phase-1 kernel: the position-major one unless SBG_FILTER=sweep asks for the bitmap sweep.
@@ -449,7 +548,7 @@ int run_filter7(sbg_handle *h, int part, int nparts, uint32_t *count_out) {
     if ((rc = reset_ctl(h)) != SBG_OK) return rc;
     cudaEventRecord(h->ev[0], h->stream);
     if (use_position_major(h)) {
-      if ((rc = launch_filter7_pm(h, part, nparts, max_warps)) != SBG_OK) return rc;
+      if ((rc = launch_filter7_pm(h, part, nparts, attempt > 0)) != SBG_OK) return rc;
     } else if ((rc = launch_sweep<5>(h, part, nparts, max_warps)) != SBG_OK) {
       return rc;
     }
@@ -760,6 +859,7 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_BATCH") != nullptr) h->opt_batch = atoi(getenv("SBG_BATCH"));
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
   if (getenv("SBG_FILTER") != nullptr) h->opt_filter = strcmp(getenv("SBG_FILTER"), "sweep") == 0;
+  if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
   if (getenv("SBG_SEARCH5") != nullptr) {
     h->opt_search5 = strcmp(getenv("SBG_SEARCH5"), "two") == 0 ? 2 : 1;
   }
@@ -831,6 +931,7 @@ int sbg_use_problem(sbg_handle *h, int slot) {
   h->mask = hp.mask;
   h->n = hp.n;
   h->nw = hp.nw;
+  h->inmask = hp.inmask;
   h->problem_ready = true;
   h->list_ready = false;
   h->list_count = 0;
@@ -1115,7 +1216,7 @@ int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle
   if ((rc = launch_prepare7(h)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[0], h->stream);
   if (use_position_major(h)) {
-    if ((rc = launch_filter7_pm(h, 0, 1, 0)) != SBG_OK) return rc;
+    if ((rc = launch_filter7_pm(h, 0, 1, false)) != SBG_OK) return rc;
   } else if ((rc = launch_sweep<5>(h, 0, 1, 0)) != SBG_OK) {
     return rc;
   }

@@ -55,6 +55,7 @@ struct DevCtl {
   unsigned int list_count;         // written by k_sort_small: entries of the sorted list
   unsigned int sorted_ok;          // 1 if k_sort_small produced the sorted list on the device
   unsigned int pad;
+  unsigned long long chunk_ticket; // filter7: next (prefix, chunk) item of the chunked phase
 };
 
 // Per-call parameters of the 7-LUT decomposition.  The host supplies where each function sits in
@@ -431,7 +432,13 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
           continue;
         }
         // search_5lut: try the 10 orderings x 256 outer functions on each feasible tuple
-        // (lut.c:189-230), here, one after the other.
+        // (lut.c:189-230), here, one after the other -- unless a match in an earlier prefix is
+        // already known (dense states: every warp of the first wave sits on feasible tuples).
+        {
+          unsigned long long st = 0;
+          if (lane == 0) st = volatile_load(&ctl->stop_ticket);
+          if (gt > __shfl_sync(kFull, st, 0)) warp_done = true;
+        }
         while (fb != 0 && !warp_done) {
           const int src = __ffs(fb) - 1;
           fb &= fb - 1;
@@ -524,9 +531,24 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 template <int NW, int W, int P, bool FS>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
-    int nparts, unsigned long long list_cap, int batch, int max_warps) {
+    int nparts, unsigned long long list_cap, int batch, int max_warps,
+    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix) {
   constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
+  // Two ways of handing out the work, both in lexicographic order with the same stop rule (no new
+  // item once the list cap is reached; what was handed out is finished):
+  //  * chunked (chunks_per_prefix > 0): items are (prefix, chunk of 32 lane items) pairs over the
+  //    prefixes made of ALLOWED gates only (inbits skipped in the enumeration).  Little work in
+  //    flight, so a list that fills from the first prefixes -- small masks, where most
+  //    combinations are feasible -- ends the sweep after microseconds, whatever n is.
+  //  * by prefix (chunks_per_prefix == 0): batches of whole prefixes from prefix rank t_offset on;
+  //    less bookkeeping per combination, the form for sweeps that have to cover everything.
+  // The host launches the chunked form over the first prefixes (all of them for large n) and the
+  // prefix form behind it; the latter gives up at once if the list is already full.
+  const bool chunked = chunks_per_prefix > 0;
+  if (!chunked && __syncthreads_or(threadIdx.x == 0 && volatile_load(&ctl->hit_count) >= list_cap)) {
+    return;
+  }
   const int n = prob->n;
   const int m = prob->m;
   const int npad = (n + 3) & ~3;
@@ -557,26 +579,48 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   auto fetch = [&]() {
     if (lane == 0) {
       const bool stop = volatile_load(&ctl->hit_count) >= list_cap;
-      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+      next_b = stop ? ~0ull : atomicAdd(chunked ? &ctl->chunk_ticket : &ctl->ticket, 1ull);
     }
   };
   // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
   // would be worked on even if the cap was reached meanwhile, doubling the hits in flight.
   const bool ahead = max_warps == 0;
+  const int n_allowed = n - __popc(inmask & 0xffu);
   if (ahead) fetch();
   for (;;) {
     if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     if (b == ~0ull) break;
-    const uint64_t lt = b * (uint64_t)batch;   // dealt in blocks of kDeal prefixes, see k_sweep
-    const uint64_t t_first = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
+    uint64_t t_first, t_end;
+    uint32_t q_begin = 0, q_limit = 0xffffffffu;
+    // dealt to the parts of a sharded search in blocks of kDeal consecutive items, see k_sweep
+    const uint64_t lt = chunked ? b : b * (uint64_t)batch;
+    const uint64_t dealt = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
         + (lt % kDeal);
-    if (t_first >= total) break;
+    if (chunked) {
+      if (dealt >= chunk_items) break;
+      t_first = dealt / (uint64_t)chunks_per_prefix;
+      t_end = t_first + 1;
+      q_begin = (uint32_t)(dealt % (uint64_t)chunks_per_prefix) * 32u;
+      q_limit = q_begin + 32u;
+    } else {
+      t_first = t_offset + dealt;
+      if (t_first >= total) break;
+      t_end = min(t_first + (uint64_t)batch, total);
+    }
     if (ahead) fetch();
-    const uint64_t t_end = min(t_first + (uint64_t)batch, total);
     int pre[P];
     uint64_t unused_rank;
-    unrank_prefix<P, K>(t_first, n, pre, unused_rank);
+    unrank_prefix<P, K>(t_first, chunked ? n_allowed : n, pre, unused_rank);
+    if (chunked) {   // index among the allowed gates -> gate number (excluded gates are < 8)
+#pragma unroll
+      for (int i = 0; i < P; i++) {
+        int g = pre[i];
+#pragma unroll
+        for (int bit = 0; bit < 8; bit++) g += (((inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
+        pre[i] = g;
+      }
+    }
     for (uint64_t gt = t_first; gt < t_end; gt++) {
       if (gt != t_first) {
         int i = P - 1;
@@ -587,7 +631,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
       const int last = pre[P - 1];
       const int r = n - last - 2;                   // candidates for (e,)f: last+1 .. n-2
       const uint32_t Q = P == 4 ? (uint32_t)(r * (r - 1) / 2) : (uint32_t)r;
-      swept_local += c_binom[n - last - 1][K - P];  // 7-combinations sharing this prefix
+      if (q_begin >= max(Q, 1u)) continue;          // head launch: no such chunk in this prefix
+      if (q_begin == 0) swept_local += c_binom[n - last - 1][K - P];  // 7-combinations sharing this prefix
       bool rejected = false;
 #pragma unroll
       for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
@@ -624,7 +669,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 
       unsigned long long emitted = 0;
       bool prefix_done = false;
-      for (uint32_t q0 = 0; q0 < Q && !prefix_done; q0 += 32) {
+      for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !prefix_done; q0 += 32) {
         const uint32_t q = q0 + lane;
         bool lane_ok = q < Q;
         int pi = 0, pj = 0;

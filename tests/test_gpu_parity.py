@@ -237,6 +237,44 @@ def test_hit_buffer_overflow_is_retried(monkeypatch):
     assert whole_hash == parts_hash       # three parts (some of them retried) merge to the same list
 
 
+def test_chunked_and_prefix_forms_agree():
+    """Phase 1 hands its work out as (prefix, chunk) items over the allowed gates (head, or everything
+    in the overflow retry) and as batches of whole prefixes; SBG_HEAD = 0 / 1 / 2 forces no head / a
+    head / chunk items throughout.  Lists -- whole and merged from 3 parts -- must be identical, on
+    dense states (small masks: the cap is reached inside the first prefixes, low gates excluded) and
+    on a sparse one; the dense 5-gate-prefix case is also checked against the oracle's first entries."""
+    import json
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, json, numpy as np; sys.path[:0]=[%r, %r]\n"
+        "import _support as S, sboxgates_b200 as sb\n"
+        "eng = sb.LutEngine(0); sbox = S.rijndael_sbox(); out = []\n"
+        "cases = [(56, [(0,1),(5,0),(3,1)]), (72, [(0,1),(5,0),(3,1),(6,1)]), (50, [(2,1),(7,0)]),\n"
+        "         (130, [(1,1),(2,0),(4,1),(7,1)]), (130, [(0,0),(1,1),(3,1)])]\n"
+        "for n, fixed in cases:\n"
+        "    eng.load(S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed])\n"
+        "    whole = eng.filter7_part(0, 1)\n"
+        "    parts = np.sort(np.concatenate([eng.filter7_part(p, 3) for p in range(3)]))[:100000]\n"
+        "    out.append([len(whole), hashlib.sha1(whole.tobytes()).hexdigest(), hashlib.sha1(parts.tobytes()).hexdigest(),\n"
+        "                whole[:2000].tolist() if n == 130 and fixed[0][0] == 1 else []])\n"
+        "print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
+    outs = {}
+    for mode in ("0", "1", "2"):
+        env = dict(os.environ, SBG_HEAD=mode)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                             check=True)
+        outs[mode] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert outs["0"] == outs["1"] == outs["2"]
+    lens = [c[0] for c in outs["1"]]
+    assert lens[0] == lens[1] == lens[3] == lens[4] == 100000 and 0 < lens[2] < 100000
+    assert all(c[1] == c[2] for c in outs["1"])
+    n, fixed = 130, [(1, 1), (2, 0), (4, 1), (7, 1)]
+    want, _ = S.oracle_filter7(S.synthetic_state(n, seed=n), S.sbox_target(S.rijndael_sbox(), n % 8),
+                               S.mux_mask(fixed), [b for b, _ in fixed], cap=2000)
+    assert [sb.lut.unpack_tuple7(p) for p in outs["1"][3][3]] == want.tolist()
+
+
 def _max_size_case():
     rs = np.random.RandomState(500)
     tabs = S.synthetic_state(500, seed=500)
