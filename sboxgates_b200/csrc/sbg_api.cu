@@ -191,6 +191,7 @@ struct sbg_handle {
   int opt_search5 = 0;      // SBG_SEARCH5: 0 by size, 1 fused, 2 two kernels
   int opt_head = -1;        // SBG_HEAD: chunked phase of the 7-LUT filter, 0 none, 1 first prefixes,
                             // 2 everything (-1 = by n and mask size)
+  int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
   float ms[4] = {0, 0, 0, 0};
@@ -267,6 +268,7 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
 // problem and a nominal warp count only, never of the device a rank happens to run on.
 constexpr uint64_t kNominalWarps = 148 * 2 * kWarpsPerCta;
 
+constexpr int kSinglePrefixMaxGates = 72;
 uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   const uint64_t warps = kNominalWarps;
   if (h->opt_batch > 0) {
@@ -277,6 +279,10 @@ uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   // work per ticket in lane-items: (f,g) pairs for the sweeps (P = 3, 5), (e,f) pairs for the
   // position-major kernel with 4-gate prefixes (P = 4), single f for its 5-gate form (P = 6)
   const bool pm = P == 4 || P == 6;
+  // position-major kernel, 4-gate prefixes: single prefixes up to n = 72 (measured, scripts/
+  // sweep_head.sh / sweep_batch.sh: n = 48 / 64 full mask 1.07 / 7.08 ms against 1.26 / 8.99 ms with
+  // the formula below; from n = 80 on the formula's 4 is as good or better)
+  if (P == 4 && n <= kSinglePrefixMaxGates) return 1;
   const uint64_t total = pm ? h_binom[n - 1][6] : h_binom[n][P + 2];
   const uint64_t avg_pairs = std::max<uint64_t>(1, total / std::max<uint64_t>(1, tickets));
   const uint64_t qmax = P == 6 ? (uint64_t)std::max(1, n - 7) : h_binom[n - P - (P == 4 ? 1 : 0)][2];
@@ -367,8 +373,9 @@ ChunkPlan plan_chunks(const sbg_handle *h, int m, bool retry) {
   pl.chunks = (int)std::max<uint64_t>(1, (qmax + 31) / 32);
   uint64_t prefixes = total_c;
   if (mode == 1) {
+    const uint64_t waves = h->opt_head_waves > 0 ? (uint64_t)h->opt_head_waves : kHeadWaves;
     prefixes = std::min<uint64_t>(total_c,
-        std::max<uint64_t>(1, kHeadWaves * kNominalWarps / (uint64_t)pl.chunks));
+        std::max<uint64_t>(1, waves * kNominalWarps / (uint64_t)pl.chunks));
   }
   pl.items = prefixes * (uint64_t)pl.chunks;
   pl.all = prefixes == total_c;
@@ -419,28 +426,20 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, bool retry) {
   const int max_warps = !retry ? 0 : (int)std::max<size_t>(1, pl.all
       ? (h->hits_cap - SBG_LIST_CAP) / kPerChunkMax : h->hits_cap / kPerPrefixMax - 1);
   const uint64_t tickets = pl.all ? 0 : (total - pl.t_offset + nparts - 1) / nparts;
-  const uint64_t chunk_tickets = (pl.items + nparts - 1) / nparts;
+  // chunk tickets of one part: whole deal blocks, the same count for every part
+  const uint64_t chunk_tickets = (pl.items + kDeal * nparts - 1) / (kDeal * nparts) * kDeal;
 #define SBG_LAUNCH_PM(NWV, WV, FSV)                                                            \
   {                                                                                            \
     const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
-    if (pl.items > 0) {                                                                        \
-      int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, chunk_tickets);              \
-      if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta); \
-      k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,  \
-          h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, 1, max_warps, 0ull,  \
-          pl.items, pl.chunks);                                                                \
-      h->launches++;                                                                           \
-    }                                                                                          \
-    if (!pl.all) {                                                                             \
-      int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets);                    \
-      if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta); \
-      uint64_t bsz = pick_batch(h, tickets, n, P == 4 ? 4 : 6);                                \
-      if (max_warps > 0) bsz = 1;                                                              \
-      k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,  \
-          h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps, \
-          pl.t_offset, 0ull, 0);                                                               \
-      h->launches++;                                                                           \
-    }                                                                                          \
+    int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets + chunk_tickets);      \
+    if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
+    uint64_t bsz = pl.all ? 1 : pick_batch(h, tickets, n, P == 4 ? 4 : 6);                     \
+    if (max_warps > 0) bsz = 1;                                                                \
+    k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,    \
+        h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
+        pl.all ? (unsigned long long)total : pl.t_offset, pl.items, std::max(1, pl.chunks),    \
+        chunk_tickets);                                                                        \
+    h->launches++;                                                                             \
   }
   if (n <= 31) {         // one word of candidate gates per pass, its top bit free
     switch (h->nw) {
@@ -860,6 +859,7 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
   if (getenv("SBG_FILTER") != nullptr) h->opt_filter = strcmp(getenv("SBG_FILTER"), "sweep") == 0;
   if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
+  if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));
   if (getenv("SBG_SEARCH5") != nullptr) {
     h->opt_search5 = strcmp(getenv("SBG_SEARCH5"), "two") == 0 ? 2 : 1;
   }

@@ -55,7 +55,6 @@ struct DevCtl {
   unsigned int list_count;         // written by k_sort_small: entries of the sorted list
   unsigned int sorted_ok;          // 1 if k_sort_small produced the sorted list on the device
   unsigned int pad;
-  unsigned long long chunk_ticket; // filter7: next (prefix, chunk) item of the chunked phase
 };
 
 // Per-call parameters of the 7-LUT decomposition.  The host supplies where each function sits in
@@ -532,23 +531,21 @@ template <int NW, int W, int P, bool FS>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
     int nparts, unsigned long long list_cap, int batch, int max_warps,
-    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix) {
+    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix,
+    unsigned long long chunk_tickets) {
   constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
-  // Two ways of handing out the work, both in lexicographic order with the same stop rule (no new
-  // item once the list cap is reached; what was handed out is finished):
-  //  * chunked (chunks_per_prefix > 0): items are (prefix, chunk of 32 lane items) pairs over the
-  //    prefixes made of ALLOWED gates only (inbits skipped in the enumeration).  Little work in
-  //    flight, so a list that fills from the first prefixes -- small masks, where most
-  //    combinations are feasible -- ends the sweep after microseconds, whatever n is.
-  //  * by prefix (chunks_per_prefix == 0): batches of whole prefixes from prefix rank t_offset on;
-  //    less bookkeeping per combination, the form for sweeps that have to cover everything.
-  // The host launches the chunked form over the first prefixes (all of them for large n) and the
-  // prefix form behind it; the latter gives up at once if the list is already full.
-  const bool chunked = chunks_per_prefix > 0;
-  if (!chunked && __syncthreads_or(threadIdx.x == 0 && volatile_load(&ctl->hit_count) >= list_cap)) {
-    return;
-  }
+  // Work is handed out through one ordered ticket counter, in lexicographic order, under one stop
+  // rule (no new ticket once the list cap is reached; what was handed out is finished).  Two kinds
+  // of ticket:
+  //  * the first chunk_tickets tickets are (prefix, chunk of 32 lane items) pairs over the first
+  //    prefixes made of ALLOWED gates only (inbits skipped in the enumeration).  They are the
+  //    heaviest prefixes, so this spreads the kernel's longest items over many warps; and because
+  //    little work is in flight, a list that fills from the first prefixes -- small masks, where
+  //    most combinations are feasible -- ends the sweep after microseconds, whatever n is;
+  //  * the rest are batches of whole prefixes from prefix rank t_offset on (the first prefix the
+  //    chunk tickets do not cover): less bookkeeping per combination, the form for sweeps that
+  //    have to cover everything.
   const int n = prob->n;
   const int m = prob->m;
   const int npad = (n + 3) & ~3;
@@ -579,7 +576,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   auto fetch = [&]() {
     if (lane == 0) {
       const bool stop = volatile_load(&ctl->hit_count) >= list_cap;
-      next_b = stop ? ~0ull : atomicAdd(chunked ? &ctl->chunk_ticket : &ctl->ticket, 1ull);
+      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
     }
   };
   // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
@@ -594,11 +591,15 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     uint64_t t_first, t_end;
     uint32_t q_begin = 0, q_limit = 0xffffffffu;
     // dealt to the parts of a sharded search in blocks of kDeal consecutive items, see k_sweep
-    const uint64_t lt = chunked ? b : b * (uint64_t)batch;
+    const bool chunked = b < chunk_tickets;
+    const uint64_t lt = chunked ? b : (b - chunk_tickets) * (uint64_t)batch;
     const uint64_t dealt = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
         + (lt % kDeal);
     if (chunked) {
-      if (dealt >= chunk_items) break;
+      if (dealt >= chunk_items) {   // the last deal block is shorter for some parts
+        if (ahead) fetch();
+        continue;
+      }
       t_first = dealt / (uint64_t)chunks_per_prefix;
       t_end = t_first + 1;
       q_begin = (uint32_t)(dealt % (uint64_t)chunks_per_prefix) * 32u;
