@@ -191,6 +191,7 @@ struct sbg_handle {
   int opt_search5 = 0;      // SBG_SEARCH5: 0 by size, 1 fused, 2 two kernels
   int opt_head = -1;        // SBG_HEAD: chunked phase of the 7-LUT filter, 0 none, 1 first prefixes,
                             // 2 everything (-1 = by n and mask size)
+  int opt_shift = -1;       // SBG_SHIFT: phase-1 shifted single-word windows, 0 never, 1 whenever n <= 63
   int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   uint64_t launches = 0;      // our kernels
   uint64_t lib_launches = 0;  // CUB radix-sort kernels
@@ -269,6 +270,10 @@ int grid_for(sbg_handle *h, Kernel kernel, size_t smem, uint64_t work_items_in_w
 constexpr uint64_t kNominalWarps = 148 * 2 * kWarpsPerCta;
 
 constexpr int kSinglePrefixMaxGates = 72;
+// Shifted single-word windows in phase 1 up to here (SBG_SHIFT=0|1 overrides).  Measured against
+// the aligned two-word windows, full mask (scripts/sweep_shift.sh): n = 32 / 40 / 48 / 56 / 63:
+// 0.111 / 0.338 / 1.045 / 2.146 / 4.369 ms -> 0.086 / 0.287 / 0.869 / 1.958 / 4.301 ms.
+constexpr int kShiftMaxGates = 60;
 uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   const uint64_t warps = kNominalWarps;
   if (h->opt_batch > 0) {
@@ -323,10 +328,11 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
 }
 
 template <int NW, int P>
-size_t filter_pm_smem(int n, int m) {
+size_t filter_pm_smem(int n, int m, bool shifted = false) {
   const int npad = (n + 3) & ~3;
   const int ngw = (((n + 31) >> 5) + 1) & ~1;
-  return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3) + kWarpsPerCta * (1 << P) * NW);
+  return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3) + kWarpsPerCta * (1 << P) * NW
+      + (shifted ? kWarpsPerCta * m : 0));
 }
 
 // Position-major phase 1 (k_filter7_pm): work items are 4- or 5-gate prefixes.  The 5-gate form does
@@ -428,39 +434,53 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, bool retry) {
   const uint64_t tickets = pl.all ? 0 : (total - pl.t_offset + nparts - 1) / nparts;
   // chunk tickets of one part: whole deal blocks, the same count for every part
   const uint64_t chunk_tickets = (pl.items + kDeal * nparts - 1) / (kDeal * nparts) * kDeal;
-#define SBG_LAUNCH_PM(NWV, WV, FSV)                                                            \
+#define SBG_LAUNCH_PM(NWV, WV, FSV, SHV)                                                       \
   {                                                                                            \
-    const size_t smem = filter_pm_smem<NWV, P>(n, m);                                          \
-    int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV>, smem, tickets + chunk_tickets);      \
+    const size_t smem = filter_pm_smem<NWV, P>(n, m, SHV);                                     \
+    int grid = grid_for(h, k_filter7_pm<NWV, WV, P, FSV, SHV>, smem, tickets + chunk_tickets); \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
     uint64_t bsz = pl.all ? 1 : pick_batch(h, tickets, n, P == 4 ? 4 : 6);                     \
     if (max_warps > 0) bsz = 1;                                                                \
-    k_filter7_pm<NWV, WV, P, FSV><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl,    \
+    k_filter7_pm<NWV, WV, P, FSV, SHV><<<grid, kThreads, smem, h->stream>>>(h->d_prob,         \
+        h->d_ctl,                                                                              \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
         pl.all ? (unsigned long long)total : pl.t_offset, pl.items, std::max(1, pl.chunks),    \
         chunk_tickets);                                                                        \
     h->launches++;                                                                             \
   }
-  if (n <= 31) {         // one word of candidate gates per pass, its top bit free
+  const bool shifted = P == 4 && (h->opt_shift >= 0 ? h->opt_shift != 0 && n <= 63
+                                                     : n <= kShiftMaxGates);
+  if constexpr (P == 4) {
+    if (shifted) {         // one word of 31 candidate gates from the first possible g on
+      switch (h->nw) {
+        case 1: SBG_LAUNCH_PM(1, 1, true, true) break;
+        case 2: SBG_LAUNCH_PM(2, 1, true, true) break;
+        case 4: SBG_LAUNCH_PM(4, 1, true, true) break;
+        default: SBG_LAUNCH_PM(8, 1, true, true) break;
+      }
+    }
+  }
+  if (shifted) {
+  } else if (n <= 31) {  // one word of candidate gates per pass, its top bit free
     switch (h->nw) {
-      case 1: SBG_LAUNCH_PM(1, 1, true) break;
-      case 2: SBG_LAUNCH_PM(2, 1, true) break;
-      case 4: SBG_LAUNCH_PM(4, 1, true) break;
-      default: SBG_LAUNCH_PM(8, 1, true) break;
+      case 1: SBG_LAUNCH_PM(1, 1, true, false) break;
+      case 2: SBG_LAUNCH_PM(2, 1, true, false) break;
+      case 4: SBG_LAUNCH_PM(4, 1, true, false) break;
+      default: SBG_LAUNCH_PM(8, 1, true, false) break;
     }
   } else if (n <= 63) {  // two words, one pass, top bit free
     switch (h->nw) {
-      case 1: SBG_LAUNCH_PM(1, 2, true) break;
-      case 2: SBG_LAUNCH_PM(2, 2, true) break;
-      case 4: SBG_LAUNCH_PM(4, 2, true) break;
-      default: SBG_LAUNCH_PM(8, 2, true) break;
+      case 1: SBG_LAUNCH_PM(1, 2, true, false) break;
+      case 2: SBG_LAUNCH_PM(2, 2, true, false) break;
+      case 4: SBG_LAUNCH_PM(4, 2, true, false) break;
+      default: SBG_LAUNCH_PM(8, 2, true, false) break;
     }
   } else {
     switch (h->nw) {
-      case 1: SBG_LAUNCH_PM(1, 2, false) break;
-      case 2: SBG_LAUNCH_PM(2, 2, false) break;
-      case 4: SBG_LAUNCH_PM(4, 2, false) break;
-      default: SBG_LAUNCH_PM(8, 2, false) break;
+      case 1: SBG_LAUNCH_PM(1, 2, false, false) break;
+      case 2: SBG_LAUNCH_PM(2, 2, false, false) break;
+      case 4: SBG_LAUNCH_PM(4, 2, false, false) break;
+      default: SBG_LAUNCH_PM(8, 2, false, false) break;
     }
   }
 #undef SBG_LAUNCH_PM
@@ -859,6 +879,7 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
   if (getenv("SBG_FILTER") != nullptr) h->opt_filter = strcmp(getenv("SBG_FILTER"), "sweep") == 0;
   if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
+  if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;
   if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));
   if (getenv("SBG_SEARCH5") != nullptr) {
     h->opt_search5 = strcmp(getenv("SBG_SEARCH5"), "two") == 0 ? 2 : 1;

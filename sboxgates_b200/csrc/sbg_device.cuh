@@ -527,7 +527,12 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 // unused (n <= 31 with W = 1, n <= 63 with W = 2), the host stores the position's target bit there;
 // the AND / OR accumulators then also tell which targets a part has seen (OR = some 1, AND = only 1s)
 // and the separate bookkeeping disappears from the inner loop.
-template <int NW, int W, int P, bool FS>
+// SH ("shifted window", n <= 63, W = 1, FS): at small n a lane has few candidate last gates -- all of
+// them above the prefix -- so instead of aligned 64-gate windows the warp builds, per prefix, a copy
+// of the rows shifted down to the first possible g (31 gates per word, the target bit on top) in
+// its own shared-memory scratch; one word per position then covers every candidate of nearly every
+// prefix and the position loop does half the accumulates.
+template <int NW, int W, int P, bool FS, bool SH = false>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
     int nparts, unsigned long long list_cap, int batch, int max_warps,
@@ -555,6 +560,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint32_t *cells = s_xr + ((m * ngw + 3) & ~3) + warp * (NC * NW);
+  uint32_t *sx = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW) + warp * m;   // SH only
+  static_assert(!SH || (W == 1 && P == 4 && FS), "shifted windows: one word, 4-gate prefixes, n <= 63");
 
   for (int i = threadIdx.x; i < m * ngw; i += blockDim.x) {
     s_xr[i] = prob->xr[i / ngw][i % ngw];
@@ -670,6 +677,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 
       unsigned long long emitted = 0;
       bool prefix_done = false;
+      int built = -1;   // SH: window whose shifted rows are in sx
       for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !prefix_done; q0 += 32) {
         const uint32_t q = q0 + lane;
         bool lane_ok = q < Q;
@@ -690,17 +698,41 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
           tf[w] = s_tabs[w * npad + gf];
         }
         // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
-        for (int wb = ((last + (K - P)) >> 5) & ~(W - 1); wb < ((n + 31) >> 5); wb += W) {
+        // (SH: windows of 31 gates starting AT the smallest possible g, wb counts them)
+        const int first_g = last + (K - P);
+        for (int wb = SH ? 0 : ((first_g >> 5) & ~(W - 1));
+             SH ? (first_g + 31 * wb < n) : (wb < ((n + 31) >> 5)); wb += W) {
+          const int base = SH ? first_g + 31 * wb : 0;
           uint32_t V[W];
+          if constexpr (SH) {
+            if (built != wb) {   // this warp's shifted rows for the window (one build per prefix, mostly)
+              __syncwarp();
+              for (int pp = lane; pp < m; pp += 32) {
+                const uint32_t lo = s_xr[pp * ngw], hi = s_xr[pp * ngw + 1];
+                const uint32_t tb = (n <= 31 ? lo : hi) & 0x80000000u;   // the row's target bit
+                const uint32_t v = base < 32 ? __funnelshift_r(lo, hi, base) : (hi >> (base - 32));
+                sx[pp] = (v & 0x7fffffffu) | tb;
+              }
+              __syncwarp();
+              built = wb;
+            }
+            uint32_t v = 0x7fffffffu;                // gates base .. base+30: keep gf < g < n
+            if (n - base < 31) v = 0x7fffffffu >> (31 - (n - base));
+            if (gf + 1 - base >= 31) v = 0u;
+            else if (gf + 1 - base > 0) v &= 0xffffffffu << (gf + 1 - base);
+            if (base < 8) v &= ~(inmask >> base);
+            V[0] = lane_ok ? v : 0u;
+          } else {
 #pragma unroll
-          for (int j = 0; j < W; j++) {
-            const int g0 = (wb + j) * 32;           // gates g0 .. g0+31: keep gf < g < n
-            uint32_t v = 0xffffffffu;
-            if (n - g0 < 32) v = (n - g0 <= 0) ? 0u : (0xffffffffu >> (32 - (n - g0)));
-            if (gf + 1 - g0 >= 32) v = 0u;
-            else if (gf + 1 - g0 > 0) v &= 0xffffffffu << (gf + 1 - g0);
-            if (g0 == 0) v &= ~inmask;
-            V[j] = lane_ok ? v : 0u;
+            for (int j = 0; j < W; j++) {
+              const int g0 = (wb + j) * 32;           // gates g0 .. g0+31: keep gf < g < n
+              uint32_t v = 0xffffffffu;
+              if (n - g0 < 32) v = (n - g0 <= 0) ? 0u : (0xffffffffu >> (32 - (n - g0)));
+              if (gf + 1 - g0 >= 32) v = 0u;
+              else if (gf + 1 - g0 > 0) v &= 0xffffffffu << (gf + 1 - g0);
+              if (g0 == 0) v &= ~inmask;
+              V[j] = lane_ok ? v : 0u;
+            }
           }
           bool alive = false;
 #pragma unroll
@@ -737,6 +769,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                   const uint2 xx = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
                   x[0] = xx.x;
                   x[W - 1] = xx.y;
+                } else if (SH) {
+                  x[0] = sx[p];
                 } else {
                   x[0] = s_xr[p * ngw + wb];
                 }
@@ -814,7 +848,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
               const int gbit = __ffs(v) - 1;
               v &= v - 1;
               if (base_slot < hits_cap) {
-                hits[base_slot] = head | (uint64_t)((wb + j) * 32 + gbit);
+                hits[base_slot] = head | (uint64_t)(SH ? base + gbit : (wb + j) * 32 + gbit);
               } else {
                 atomicExch(&ctl->overflow, 1u);
               }
