@@ -141,6 +141,26 @@ __device__ __forceinline__ void unrank_pair(uint32_t q, int r, int &i, int &j) {
   j = ii + 1 + (int)(q - (uint32_t)(ii * (2 * r - ii - 1) / 2));
 }
 
+// Leading zeros of a non-zero word in one instruction (FLO.SH); __clz pays a subtraction for x == 0.
+__device__ __forceinline__ int clz_nonzero(uint32_t x) {
+  int c;
+  asm("bfind.shiftamt.u32 %0, %1;" : "=r"(c) : "r"(x));
+  return c;
+}
+
+// Shared-memory load from a 32-bit shared-window address (one address instruction in the caller).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
 }
@@ -562,6 +582,12 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   uint32_t *cells = s_xr + ((m * ngw + 3) & ~3) + warp * (NC * NW);
   uint32_t *sx = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW) + warp * m;   // SH only
   static_assert(!SH || (W == 1 && P == 4 && FS), "shifted windows: one word, 4-gate prefixes, n <= 63");
+  const uint32_t sx_top = (uint32_t)__cvta_generic_to_shared(sx + 31);   // row 31 of word 0
+  const uint32_t xr_base = (uint32_t)__cvta_generic_to_shared(s_xr);
+  const uint32_t neg_row_bytes = 0u - (uint32_t)ngw * 4u;   // one multiply-add per address
+  // 0x7fffffff held in a register: as a literal the compiler re-creates it at every position
+  // (max_warps is never negative; the arithmetic only hides the constant from constant folding)
+  const uint32_t low31 = 0x7fffffffu ^ ((uint32_t)max_warps >> 31);
 
   for (int i = threadIdx.x; i < m * ngw; i += blockDim.x) {
     s_xr[i] = prob->xr[i / ngw][i % ngw];
@@ -754,23 +780,27 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 #pragma unroll
             for (int w = 0; w < NW; w++) {
               uint32_t bits = cells[cj * NW + w];
+              // shared-window address of row w*32+31 of this window (aligned two-word windows)
+              const uint32_t row_top = xr_base + (uint32_t)((w * 32 + 31) * ngw + wb) * 4u;
               while (bits != 0) {                     // warp-uniform loop over the cell's positions
-                const int j = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int p = w * 32 + j;
-                const uint32_t tp = (T[w] >> j) & 1u;
+                // from the top bit down: the leading-zero count is at once the shift that brings
+                // the position's bit of a table to the sign position
+                const int c = clz_nonzero(bits);
+                bits &= low31 >> c;
+                const int p = w * 32 + 31 - c;
+                const uint32_t tp = (T[w] << c) >> 31;
                 // eb / fb = bit j of the lane's e / f table spread over a whole word (shift it to
                 // the sign position, arithmetic shift back): all-ones / zero masks without a
                 // predicate, so that every masked accumulate below is ONE three-input LOP3.
-                const uint32_t fb = (uint32_t)((int32_t)(tf[w] << (31 - j)) >> 31);
-                const uint32_t eb = P == 4 ? (uint32_t)((int32_t)(te[w] << (31 - j)) >> 31) : 0u;
+                const uint32_t fb = (uint32_t)((int32_t)(tf[w] << c) >> 31);
+                const uint32_t eb = P == 4 ? (uint32_t)((int32_t)(te[w] << c) >> 31) : 0u;
                 uint32_t x[W];
                 if (W == 2) {
-                  const uint2 xx = *reinterpret_cast<const uint2 *>(s_xr + p * ngw + wb);
+                  const uint2 xx = lds_v2(row_top + neg_row_bytes * (uint32_t)c);
                   x[0] = xx.x;
                   x[W - 1] = xx.y;
                 } else if (SH) {
-                  x[0] = sx[p];
+                  x[0] = lds_u32(sx_top + (uint32_t)(w * 128) - 4u * (uint32_t)c);
                 } else {
                   x[0] = s_xr[p * ngw + wb];
                 }
