@@ -142,7 +142,7 @@ struct sbg_handle {
   };
   DevCall *d_call = nullptr;
   DevCall *h_call = nullptr;     // pinned
-  DevCtl *d_ctl = nullptr;       // = &d_call->ctl
+  DevCtl *d_ctl = nullptr;       // header of d_sorted_block
   DevCtl *h_ctl = nullptr;       // = &h_call->ctl
   DevParams7 *d_par7 = nullptr;  // = &d_call->par
   DevParams7 *h_par7 = nullptr;  // = &h_call->par
@@ -153,6 +153,7 @@ struct sbg_handle {
   uint8_t *h_pos5 = nullptr;     // pinned
 
   uint64_t *d_hits = nullptr;    // unordered feasible tuples of this device
+  char *d_sorted_block = nullptr;  // [control words, 128 B][sorted list]
   uint64_t *d_sorted = nullptr;  // sorted copy
   uint64_t *d_list = nullptr;    // installed list (points into d_sorted or d_hits)
   size_t hits_cap = 0;
@@ -534,9 +535,15 @@ int reset_ctl(sbg_handle *h) {
   return SBG_OK;
 }
 
-int fetch_ctl(sbg_handle *h) {
-  SBG_CUDA(h, cudaMemcpyAsync(h->h_ctl_out, h->d_ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost,
-      h->stream));
+// The control words sit in a 128-byte header in front of the sorted list, so that one copy brings
+// back both them and (with_head) the first kHeadEntries list entries.
+constexpr size_t kCtlHeaderBytes = 128;
+static_assert(sizeof(DevCtl) <= kCtlHeaderBytes, "control words must fit the header");
+
+int fetch_ctl(sbg_handle *h, bool with_head = false) {
+  SBG_CUDA(h, cudaMemcpyAsync(h->h_ctl_out, h->d_ctl,
+      with_head ? kCtlHeaderBytes + kHeadEntries * sizeof(uint64_t) : sizeof(DevCtl),
+      cudaMemcpyDeviceToHost, h->stream));
   SBG_CUDA(h, cudaStreamSynchronize(h->stream));
   *h->h_ctl = *h->h_ctl_out;
   return SBG_OK;
@@ -611,8 +618,13 @@ void build_params7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *mid
 // (DevParams7::minpos3 is built on the device by k_prepare7).
 constexpr size_t kCallUploadBytes = offsetof(sbg_handle::DevCall, par) + offsetof(DevParams7, minpos3);
 
-int launch_prepare7(sbg_handle *h) {
-  k_prepare7<<<1, 1024, 0, h->stream>>>(h->d_par7);
+// h->h_par7 holds the two inverse permutations (build_params7); they go to the device as kernel
+// arguments.  reset: also reset the control words (first kernel of a call).
+int launch_prepare7(sbg_handle *h, bool reset) {
+  Pos512 pos;
+  memcpy(pos.outer, h->h_par7->pos_outer, 256);
+  memcpy(pos.middle, h->h_par7->pos_middle, 256);
+  k_prepare7<<<1, 1024, 0, h->stream>>>(h->d_par7, h->d_ctl, pos, reset ? 1 : 0);
   h->launches++;
   SBG_CUDA(h, cudaGetLastError());
   return SBG_OK;
@@ -625,10 +637,7 @@ int run_decomp7(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
   h->ms[3] = 0.f;
   if (h->list_count == 0) return SBG_OK;
   build_params7(h, outer_order, middle_order);
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_par7, h->h_par7, offsetof(DevParams7, minpos3),
-      cudaMemcpyHostToDevice, h->stream));
-  if ((rc = reset_ctl(h)) != SBG_OK) return rc;
-  if ((rc = launch_prepare7(h)) != SBG_OK) return rc;
+  if ((rc = launch_prepare7(h, true)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[4], h->stream);
   if ((rc = launch_decomp7(h, part, nparts)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[5], h->stream);
@@ -666,10 +675,11 @@ int run_search5(sbg_handle *h, int part, int nparts, const uint8_t *func_order, 
   int rc;
   const uint64_t two_kernel_max = 4000000;  // C(n,5) up to n = 52
   bool two = h->opt_search5 != 0 ? h->opt_search5 == 2 : h_binom[h->n][5] <= two_kernel_max;
-  for (int pos = 0; pos < 256; pos++) h->h_pos5[func_order[pos]] = (uint8_t)pos;
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_pos5, h->h_pos5, 256, cudaMemcpyHostToDevice, h->stream));
+  Pos256 pos5;
+  for (int pos = 0; pos < 256; pos++) pos5.b[func_order[pos]] = (uint8_t)pos;
   for (;;) {
-    if ((rc = reset_ctl(h)) != SBG_OK) return rc;
+    k_begin5<<<1, 256, 0, h->stream>>>(h->d_ctl, h->d_pos5, pos5);
+    h->launches++;
     cudaEventRecord(h->ev[6], h->stream);
     if ((rc = launch_sweep<3>(h, part, nparts, 0, two)) != SBG_OK) return rc;
     if (two && (rc = launch_decomp5(h)) != SBG_OK) return rc;
@@ -866,12 +876,11 @@ int sbg_create(sbg_handle **out, int device) {
   SBG_CUDA(h, cudaMallocHost(&h->h_prob, sizeof(DevProblem)));
   SBG_CUDA(h, cudaMalloc(&h->d_call, sizeof(sbg_handle::DevCall)));
   SBG_CUDA(h, cudaMallocHost(&h->h_call, sizeof(sbg_handle::DevCall)));
-  h->d_ctl = &h->d_call->ctl;
   h->h_ctl = &h->h_call->ctl;
   h->d_par7 = &h->d_call->par;
   h->h_par7 = &h->h_call->par;
-  SBG_CUDA(h, cudaMallocHost(&h->h_ctl_out, sizeof(DevCtl)));
-  SBG_CUDA(h, cudaMallocHost(&h->h_head, kHeadEntries * sizeof(uint64_t)));
+  SBG_CUDA(h, cudaMallocHost(&h->h_ctl_out, kCtlHeaderBytes + kHeadEntries * sizeof(uint64_t)));
+  h->h_head = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(h->h_ctl_out) + kCtlHeaderBytes);
   SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
   SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
   stamp("small buffers + pinned");
@@ -888,7 +897,9 @@ int sbg_create(sbg_handle **out, int device) {
   h->hits_cap = cap_env != nullptr ? (size_t)strtoull(cap_env, nullptr, 10) : ((size_t)32 << 20);
   if (h->hits_cap < 3 * kPerPrefixMax) h->hits_cap = 3 * kPerPrefixMax;
   SBG_CUDA(h, cudaMalloc(&h->d_hits, h->hits_cap * sizeof(uint64_t)));
-  SBG_CUDA(h, cudaMalloc(&h->d_sorted, h->hits_cap * sizeof(uint64_t)));
+  SBG_CUDA(h, cudaMalloc(&h->d_sorted_block, kCtlHeaderBytes + h->hits_cap * sizeof(uint64_t)));
+  h->d_ctl = reinterpret_cast<DevCtl *>(h->d_sorted_block);
+  h->d_sorted = reinterpret_cast<uint64_t *>(h->d_sorted_block + kCtlHeaderBytes);
   h->cub_bytes = 0;
   SBG_CUDA(h, cub::DeviceRadixSort::SortKeys(nullptr, h->cub_bytes, h->d_hits, h->d_sorted,
       (int)h->hits_cap, 0, 63, h->stream));
@@ -905,10 +916,10 @@ void sbg_destroy(sbg_handle *h) {
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_slots); cudaFreeHost(h->h_prob);
     cudaFree(h->d_call); cudaFreeHost(h->h_call);
-    cudaFreeHost(h->h_ctl_out); cudaFreeHost(h->h_head);
+    cudaFreeHost(h->h_ctl_out);
     cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
     cudaFree(h->d_tab);
-    cudaFree(h->d_hits); cudaFree(h->d_sorted); cudaFree(h->d_cub);
+    cudaFree(h->d_hits); cudaFree(h->d_sorted_block); cudaFree(h->d_cub);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
     cudaStreamDestroy(h->own_stream);
   }
@@ -1228,13 +1239,7 @@ int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle
   SBG_CUDA(h, cudaSetDevice(h->device));
   int rc;
   build_params7(h, outer_order, middle_order);
-  DevCtl *c = h->h_ctl;
-  memset(c, 0, sizeof(*c));
-  c->best = ~0ull;
-  c->stop_ticket = ~0ull;
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_call, h->h_call, kCallUploadBytes, cudaMemcpyHostToDevice,
-      h->stream));
-  if ((rc = launch_prepare7(h)) != SBG_OK) return rc;
+  if ((rc = launch_prepare7(h, true)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[0], h->stream);
   if (use_position_major(h)) {
     if ((rc = launch_filter7_pm(h, 0, 1, false)) != SBG_OK) return rc;
@@ -1249,9 +1254,7 @@ int sbg_search7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *middle
   h->d_list = h->d_sorted;
   if ((rc = launch_decomp7(h, 0, 1, true)) != SBG_OK) return rc;
   cudaEventRecord(h->ev[5], h->stream);
-  SBG_CUDA(h, cudaMemcpyAsync(h->h_head, h->d_sorted, kHeadEntries * sizeof(uint64_t),
-      cudaMemcpyDeviceToHost, h->stream));
-  if ((rc = fetch_ctl(h)) != SBG_OK) return rc;
+  if ((rc = fetch_ctl(h, true)) != SBG_OK) return rc;
   h->ms[1] = elapsed(h, 0, 1);
   h->ms[2] = elapsed(h, 1, 4);
   h->ms[3] = elapsed(h, 4, 5);

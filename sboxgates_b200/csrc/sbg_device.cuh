@@ -900,9 +900,38 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 // Builds DevParams7::minpos3 from pos_middle (one CTA): entry (S,V) is the minimum, over the
 // completions of V on the bits outside S, of that function's position -- 4^8 lookups in all, no
 // synchronisation between entries.
-__global__ void __launch_bounds__(1024) k_prepare7(DevParams7 *__restrict__ par) {
+// Per-call inputs travel as kernel arguments, not as separate host->device copies: a copy-engine
+// transfer of a few hundred bytes costs several microseconds of stream latency, and a real run is
+// thousands of searches that last tens of microseconds each.
+struct Pos256 { uint8_t b[256]; };
+struct Pos512 { uint8_t outer[256]; uint8_t middle[256]; };
+
+__device__ __forceinline__ void reset_ctl_words(DevCtl *ctl) {
+  DevCtl c;
+  memset(&c, 0, sizeof(c));
+  c.best = ~0ull;
+  c.stop_ticket = ~0ull;
+  *ctl = c;
+}
+
+// First kernel of a search_5lut call: installs the position table, resets the control words.
+__global__ void __launch_bounds__(256) k_begin5(DevCtl *__restrict__ ctl, uint8_t *__restrict__ pos5,
+    const Pos256 pos) {
+  pos5[threadIdx.x] = pos.b[threadIdx.x];
+  if (threadIdx.x == 0) reset_ctl_words(ctl);
+}
+
+// First kernel of a search_7lut call / of its phase 2.  `pos` = the two inverse permutations;
+// reset != 0 also resets the control words.
+__global__ void __launch_bounds__(1024) k_prepare7(DevParams7 *__restrict__ par,
+    DevCtl *__restrict__ ctl, const Pos512 pos, int reset) {
   __shared__ uint8_t posm[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) posm[i] = par->pos_middle[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    posm[i] = pos.middle[i];
+    par->pos_middle[i] = pos.middle[i];
+    par->pos_outer[i] = pos.outer[i];
+  }
+  if (threadIdx.x == 0 && reset != 0) reset_ctl_words(ctl);
   __syncthreads();
   for (int e = threadIdx.x; e < kMinpos3; e += blockDim.x) {
     uint32_t free_bits = 0, forced = 0;
