@@ -475,12 +475,13 @@ def main():
                                    for k in ("ms5", "ms_filter", "ms_sort", "ms_decomp")},
             "e2e": {"value": (acc_e2e["T"] + acc_e2e["C"]) / (ms_e2e * 1e-3), "unit": UNIT,
                     "ms_per_step": ms_e2e / args.steps,
-                    # per state: problem block (tables + position-major copy), 5-LUT position
-                    # table + control words, 7-LUT control words + two position tables
-                    "h2d_bytes_per_step": B * (32848 + 256 + 72 + 72 + 512),
-                    # per state: control words after search_5lut; control words + first 1,024 list
+                    # per state: problem block (compressed tables, target, mask; the position-major
+                    # copy is derived on the device), 5-LUT position table and the two 7-LUT
+                    # position tables (kernel arguments)
+                    "h2d_bytes_per_step": B * (16464 + 256 + 512),
+                    # per state: control words after search_5lut; 128-byte header + first 1,024 list
                     # entries after search_7lut
-                    "d2h_bytes_per_step": B * (72 + 72 + 8192),
+                    "d2h_bytes_per_step": B * (72 + 128 + 8192),
                     "note": "host tables -> sbg_load_problem -> sbg_search5/7 -> result structs"},
             "gpu_launches": acc_res["launches"],
             "roofline": {

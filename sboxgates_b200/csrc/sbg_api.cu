@@ -171,6 +171,7 @@ struct sbg_handle {
     int nw = 0;
     uint32_t inmask = 0;
     bool ready = false;
+    bool rows_ready = false;   // DevProblem::xr built on the device
   };
   HostProblem *slots = nullptr;  // kSlots entries
   uint64_t (*tables)[4] = nullptr;
@@ -178,6 +179,7 @@ struct sbg_handle {
   uint64_t *mask = nullptr;
   int n = 0;
   int nw = 0;
+  int cur_slot = 0;
   uint32_t inmask = 0;
   bool problem_ready = false;
 
@@ -489,7 +491,23 @@ int launch_filter7_pm_p(sbg_handle *h, int part, int nparts, bool retry) {
   return SBG_OK;
 }
 
+// Position-major rows of the problem in use, built on the device the first time phase 1 needs them.
+int ensure_rows(sbg_handle *h) {
+  sbg_handle::HostProblem &hp = h->slots[h->cur_slot];
+  if (hp.rows_ready) return SBG_OK;
+  const int m = popcount256(h->mask);
+  if (m > 0) {
+    k_build_rows<<<(m * 16 + 255) / 256, 256, 0, h->stream>>>(h->d_slots + h->cur_slot);
+    h->launches++;
+    SBG_CUDA(h, cudaGetLastError());
+  }
+  hp.rows_ready = true;
+  return SBG_OK;
+}
+
 int launch_filter7_pm(sbg_handle *h, int part, int nparts, bool retry) {
+  int rc = ensure_rows(h);
+  if (rc != SBG_OK) return rc;
   const bool five = h->opt_pm_prefix != 0 ? h->opt_pm_prefix == 5 : h->n >= kPm5MinGates;
   return five ? launch_filter7_pm_p<5>(h, part, nparts, retry)
               : launch_filter7_pm_p<4>(h, part, nparts, retry);
@@ -958,6 +976,7 @@ int sbg_use_problem(sbg_handle *h, int slot) {
   sbg_handle::HostProblem &hp = h->slots[slot];
   if (!hp.ready) return fail(h, SBG_ERR_STATE, "slot %d holds no problem", slot);
   h->d_prob = h->d_slots + slot;
+  h->cur_slot = slot;
   h->tables = hp.tables;
   h->target = hp.target;
   h->mask = hp.mask;
@@ -1002,7 +1021,7 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
   hp.ready = true;
 
   DevProblem *p = h->h_prob;
-  memset(p, 0, sizeof(*p));
+  memset(p, 0, offsetof(DevProblem, xr));
   p->n = n;
   p->nw = hp.nw;
   uint32_t cm[8], ct[8], tmp[8];
@@ -1019,32 +1038,10 @@ int sbg_stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n,
   }
   p->inmask = inmask;
   p->m = m;
-  // position-major rows (see DevProblem::xr): bit g of row pos = gate g at that position,
-  // rows of target-0 positions complemented
-  for (int g = 0; g < n; g++) {
-    for (int w = 0; w < 8; w++) {
-      uint32_t bits = p->tabs[w][g];
-      while (bits != 0) {
-        const int b = __builtin_ctz(bits);
-        bits &= bits - 1;
-        p->xr[w * 32 + b][g >> 5] |= 1u << (g & 31);
-      }
-    }
-  }
-  // "free seen" (k_filter7_pm<.., FS = true>): with n <= 31 / n <= 63 the top bit of word 0 / 1 is
-  // no gate; it carries the position's target bit
-  const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
-  for (int pos = 0; pos < m; pos++) {
-    const bool t1 = ((p->T[pos >> 5] >> (pos & 31)) & 1u) != 0;
-    if (!t1) {
-      for (int w = 0; w < 16; w++) p->xr[pos][w] = ~p->xr[pos][w];
-    }
-    if (spare >= 0) {
-      uint32_t &word = p->xr[pos][spare >> 5];
-      word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
-    }
-  }
-  SBG_CUDA(h, cudaMemcpyAsync(h->d_slots + slot, p, sizeof(DevProblem), cudaMemcpyHostToDevice,
+  // The position-major rows (DevProblem::xr) are derived on the device, and only when a 7-LUT
+  // search asks for them (ensure_rows): most states of a run never get that far.
+  hp.rows_ready = false;
+  SBG_CUDA(h, cudaMemcpyAsync(h->d_slots + slot, p, offsetof(DevProblem, xr), cudaMemcpyHostToDevice,
       h->stream));
   return SBG_OK;
 }

@@ -900,6 +900,26 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 // Builds DevParams7::minpos3 from pos_middle (one CTA): entry (S,V) is the minimum, over the
 // completions of V on the bits outside S, of that function's position -- 4^8 lookups in all, no
 // synchronisation between entries.
+// Position-major rows of a staged problem (DevProblem::xr), from its gate-major tables: bit g of row
+// p = gate g at masked position p, the row complemented where the target is 0; with n <= 31 / n <= 63
+// the top bit of word 0 / 1 is no gate and carries the position's target bit ("free seen").
+__global__ void __launch_bounds__(256) k_build_rows(DevProblem *__restrict__ prob) {
+  const int n = prob->n;
+  const int m = prob->m;
+  const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m * 16) return;
+  const int p = idx >> 4, gw = idx & 15;
+  const int w = p >> 5, j = p & 31;
+  uint32_t word = 0;
+  const int g_end = min(n, gw * 32 + 32);
+  for (int g = gw * 32; g < g_end; g++) word |= ((prob->tabs[w][g] >> j) & 1u) << (g & 31);
+  const bool t1 = ((prob->T[w] >> j) & 1u) != 0;
+  if (!t1) word = ~word;
+  if (spare >= 0 && gw == (spare >> 5)) word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
+  prob->xr[p][gw] = word;
+}
+
 // Per-call inputs travel as kernel arguments, not as separate host->device copies: a copy-engine
 // transfer of a few hundred bytes costs several microseconds of stream latency, and a real run is
 // thousands of searches that last tens of microseconds each.
