@@ -302,21 +302,104 @@ uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   return b;
 }
 
+// Chunked phase of phase 1 (see k_filter7_pm): a head of kHeadWaves waves of (prefix, chunk) items
+// in front of the prefix form.  A list that fills early -- small masks make most combinations
+// feasible -- then costs microseconds instead of the first wave of whole-prefix batches, which at
+// large n is enormous (measured before: n = 200 / 300 / 500 with 16-32 masked positions took 2.6 /
+// 20 / 258 s through the overflow retry, now 0.1-0.35 ms; profiles/r01_dense_cases.md).  Sweeping
+// EVERYTHING in chunk items is much slower where the sweep has to cover the space (n = 128, 64
+// positions: 3.8 s against 0.25 s), so that form is kept for the overflow retry.  Below
+// kHeadAlwaysMinGates the head is used for small masks only, below kHeadMinGates never (measured:
+// the rijndael -o 0 run and bench.py at n = 40 are indifferent to it).
+constexpr int kHeadAlwaysMinGates = 128;
+constexpr int kHeadMaxPositions = 64;
+constexpr int kHeadMinGates = 48;
+constexpr uint64_t kHeadWaves = 64;
+constexpr uint64_t kHeadWaves5 = 16;   // search_5lut: the first match is what ends it, a short head does
+constexpr size_t kPerChunkMax = 32 * 512;   // hits one (prefix, chunk) item can emit
+
+struct ChunkPlan {
+  unsigned long long items = 0;     // (prefix, chunk) items of the chunked phase
+  int chunks = 0;                   // chunks per prefix
+  unsigned long long t_offset = 0;  // rank of the first prefix left to the prefix form
+  bool all = false;                 // the chunked phase covers everything
+};
+
+// K = size of the combinations, P = gates per prefix, mode: 0 none, 1 a head of `waves` waves of chunk
+// tickets, 2 everything in chunk tickets.
+template <int P, int K>
+ChunkPlan plan_chunks_mode(const sbg_handle *h, int mode, uint64_t waves, uint64_t qmax) {
+  ChunkPlan pl;
+  const int n = h->n;
+  const int na = n - __builtin_popcount(h->inmask & 0xffu);   // allowed gates
+  const uint64_t total_c = na >= K ? h_binom[na - (K - P)][P] : 0;
+  if (mode == 0 || total_c == 0) return pl;
+  // qmax = lane items of the first (largest) prefix
+  pl.chunks = (int)std::max<uint64_t>(1, (qmax + 31) / 32);
+  uint64_t prefixes = total_c;
+  if (mode == 1) {
+    prefixes = std::min<uint64_t>(total_c,
+        std::max<uint64_t>(1, waves * kNominalWarps / (uint64_t)pl.chunks));
+  }
+  pl.items = prefixes * (uint64_t)pl.chunks;
+  pl.all = prefixes == total_c;
+  if (!pl.all) {
+    // the first allowed prefix not covered: index `prefixes` among the P-subsets of the allowed
+    // gates, as gate numbers, ranked among the P-subsets of all gates
+    int c[P];
+    uint64_t t = prefixes;
+    const int np = na - (K - P);
+    int x = 0;
+    for (int pos = 0; pos < P; pos++) {
+      for (;; x++) {
+        const uint64_t cnt = h_binom[np - x - 1][P - pos - 1];
+        if (t < cnt) break;
+        t -= cnt;
+      }
+      c[pos] = x++;
+    }
+    for (int i = 0; i < P; i++) {
+      int g = c[i];
+      for (int bit = 0; bit < 8; bit++) g += (((h->inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
+      c[i] = g;
+    }
+    const int nr = n - (K - P);
+    uint64_t rank = 0;
+    int prev = -1;
+    for (int pos = 0; pos < P; pos++) {
+      for (int y = prev + 1; y < c[pos]; y++) rank += h_binom[nr - y - 1][P - pos - 1];
+      prev = c[pos];
+    }
+    pl.t_offset = rank;
+  }
+  return pl;
+}
+
 template <int P>
 int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 = false) {
   const int n = h->n;
-  const uint64_t tickets = (h_binom[n - 2][P] + nparts - 1) / nparts;
+  const uint64_t total = h_binom[n - 2][P];
   const unsigned long long cap = h->hits_cap;
+  // search_5lut on a large state (fused kernel): a head of chunk tickets, so that on a dense state
+  // the feasible-but-not-decomposable tuples in front of the first match are spread over the
+  // machine instead of being decomposed by the one warp that owns their prefix
+  ChunkPlan pl;
+  if (P == 3 && !emit5 && max_warps == 0 && h->opt_head != 0 && n >= kHeadAlwaysMinGates) {
+    pl = plan_chunks_mode<P, P + 2>(h, 1, kHeadWaves5, h_binom[n - 3][2]);
+  }
+  const uint64_t tickets = pl.all ? 0 : (total - pl.t_offset + nparts - 1) / nparts;
+  const uint64_t chunk_tickets = (pl.items + kDeal * nparts - 1) / (kDeal * nparts) * kDeal;
 #define SBG_LAUNCH_SWEEP(NWV)                                                                  \
   {                                                                                            \
     const size_t smem = sweep_smem<NWV, P>(n);                                                 \
-    int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets);                                    \
+    int grid = grid_for(h, k_sweep<NWV, P>, smem, tickets + chunk_tickets);                    \
     if (max_warps > 0) grid = std::min(grid, (max_warps + kWarpsPerCta - 1) / kWarpsPerCta);   \
-    uint64_t bsz = pick_batch(h, tickets, n, P);                                                  \
+    uint64_t bsz = pick_batch(h, tickets, n, P);                                               \
     if (max_warps > 0) bsz = 1;                                                                \
     k_sweep<NWV, P><<<grid, kThreads, smem, h->stream>>>(h->d_prob, h->d_ctl, h->d_pos5,       \
         h->d_hits, cap, part, nparts, (unsigned long long)SBG_LIST_CAP, (int)bsz, max_warps,   \
-        emit5, h->d_tab);                                                                      \
+        emit5, h->d_tab, pl.all ? (unsigned long long)total : pl.t_offset, pl.items,           \
+        std::max(1, pl.chunks), chunk_tickets);                                                \
   }
   switch (h->nw) {
     case 1: SBG_LAUNCH_SWEEP(1) break;
@@ -342,34 +425,9 @@ size_t filter_pm_smem(int n, int m, bool shifted = false) {
 // half the work per visited position but keeps only n-7-ish lanes of a warp busy, so it is used
 // from n = kPm5MinGates on (measured cross-over, profiles/); SBG_PM_PREFIX=4|5 overrides.
 constexpr int kPm5MinGates = 128;
-// Chunked phase of phase 1 (see k_filter7_pm): a head of kHeadWaves waves of (prefix, chunk) items
-// in front of the prefix form.  A list that fills early -- small masks make most combinations
-// feasible -- then costs microseconds instead of the first wave of whole-prefix batches, which at
-// large n is enormous (measured before: n = 200 / 300 / 500 with 16-32 masked positions took 2.6 /
-// 20 / 258 s through the overflow retry, now 0.1-0.35 ms; profiles/r01_dense_cases.md).  Sweeping
-// EVERYTHING in chunk items is much slower where the sweep has to cover the space (n = 128, 64
-// positions: 3.8 s against 0.25 s), so that form is kept for the overflow retry.  Below
-// kHeadAlwaysMinGates the head is used for small masks only, below kHeadMinGates never (measured:
-// the rijndael -o 0 run and bench.py at n = 40 are indifferent to it).
-constexpr int kHeadAlwaysMinGates = 128;
-constexpr int kHeadMaxPositions = 64;
-constexpr int kHeadMinGates = 48;
-constexpr uint64_t kHeadWaves = 64;
-constexpr size_t kPerChunkMax = 32 * 512;   // hits one (prefix, chunk) item can emit
-
-struct ChunkPlan {
-  unsigned long long items = 0;     // (prefix, chunk) items of the chunked phase
-  int chunks = 0;                   // chunks per prefix
-  unsigned long long t_offset = 0;  // rank of the first prefix left to the prefix form
-  bool all = false;                 // the chunked phase covers everything
-};
-
 template <int P>
 ChunkPlan plan_chunks(const sbg_handle *h, int m, bool retry) {
-  ChunkPlan pl;
   const int n = h->n;
-  const int na = n - __builtin_popcount(h->inmask & 0xffu);   // allowed gates
-  const uint64_t total_c = na >= 7 ? h_binom[na - (7 - P)][P] : 0;
   int mode = h->opt_head;
   if (mode < 0) {
     mode = n >= kHeadAlwaysMinGates || (m <= kHeadMaxPositions && n >= kHeadMinGates) ? 1 : 0;
@@ -377,47 +435,10 @@ ChunkPlan plan_chunks(const sbg_handle *h, int m, bool retry) {
   // overflow retry: one form for everything, so that the bound on the hits in flight is simple --
   // chunk items where a prefix is large, whole prefixes otherwise
   if (retry) mode = n >= kHeadAlwaysMinGates ? 2 : 0;
-  if (mode == 0 || total_c == 0) return pl;
+  // lane items: (e,f) pairs out of the n-5 gates that leave room for g; single f for 5-gate prefixes
   const uint64_t qmax = P == 4 ? h_binom[n - 5][2] : (uint64_t)(n - 6);
-  pl.chunks = (int)std::max<uint64_t>(1, (qmax + 31) / 32);
-  uint64_t prefixes = total_c;
-  if (mode == 1) {
-    const uint64_t waves = h->opt_head_waves > 0 ? (uint64_t)h->opt_head_waves : kHeadWaves;
-    prefixes = std::min<uint64_t>(total_c,
-        std::max<uint64_t>(1, waves * kNominalWarps / (uint64_t)pl.chunks));
-  }
-  pl.items = prefixes * (uint64_t)pl.chunks;
-  pl.all = prefixes == total_c;
-  if (!pl.all) {
-    // the first allowed prefix not covered: index `prefixes` among the P-subsets of the allowed
-    // gates, as gate numbers, ranked among the P-subsets of all gates
-    int c[P];
-    uint64_t t = prefixes;
-    const int np = na - (7 - P);
-    int x = 0;
-    for (int pos = 0; pos < P; pos++) {
-      for (;; x++) {
-        const uint64_t cnt = h_binom[np - x - 1][P - pos - 1];
-        if (t < cnt) break;
-        t -= cnt;
-      }
-      c[pos] = x++;
-    }
-    for (int i = 0; i < P; i++) {
-      int g = c[i];
-      for (int bit = 0; bit < 8; bit++) g += (((h->inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
-      c[i] = g;
-    }
-    const int nr = n - (7 - P);
-    uint64_t rank = 0;
-    int prev = -1;
-    for (int pos = 0; pos < P; pos++) {
-      for (int y = prev + 1; y < c[pos]; y++) rank += h_binom[nr - y - 1][P - pos - 1];
-      prev = c[pos];
-    }
-    pl.t_offset = rank;
-  }
-  return pl;
+  return plan_chunks_mode<P, 7>(h, mode,
+      h->opt_head_waves > 0 ? (uint64_t)h->opt_head_waves : kHeadWaves, qmax);
 }
 
 // retry: the hit buffer overflowed; run again with the number of working warps bounded so that it

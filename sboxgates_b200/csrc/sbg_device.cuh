@@ -237,11 +237,37 @@ __device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int np
 // is split, so only the "mixed" prefix cells are kept (their ones C1 = C & T and zeros C0 = C & ~T,
 // in shared memory); each must be split by f and g into four parts none of which meets both C1 and
 // C0.  A pair is dropped at the first cell it fails on.
+// Chunk tickets (see k_sweep / k_filter7_pm): the t-th P-gate prefix made of allowed gates only, as
+// gate numbers, with its rank among all prefixes (for the stop rule) and the rank of its first
+// combination (for the key).  Kept out of line: it runs once per chunk ticket, and inlined it
+// changes the code of the sweep loop around it for the worse.
+template <int P, int K>
+__device__ __noinline__ void chunk_ticket_prefix(uint64_t t, int n, uint32_t inmask, int *pre,
+    uint64_t &prefix_rank, uint64_t &base_rank) {
+  uint64_t unused_rank;
+  unrank_prefix<P, K>(t, n - __popc(inmask & 0xffu), pre, unused_rank);
+  prefix_rank = 0;
+  base_rank = 0;
+  int prev = -1;
+  for (int i = 0; i < P; i++) {
+    int g = pre[i];   // index among the allowed gates -> gate number (excluded gates are < 8)
+    for (int bit = 0; bit < 8; bit++) g += (((inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
+    pre[i] = g;
+    for (int x = prev + 1; x < g; x++) {
+      prefix_rank += c_binom[n - (K - P) - x - 1][P - i - 1];
+      base_rank += c_binom[n - x - 1][K - i - 1];
+    }
+    prev = g;
+  }
+}
+
 template <int NW, int P>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
     unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
-    int batch, int max_warps, bool emit5, const DevTables *__restrict__ tab) {
+    int batch, int max_warps, bool emit5, const DevTables *__restrict__ tab,
+    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix,
+    unsigned long long chunk_tickets) {
   constexpr int K = P + 2;
   constexpr int NC = 1 << P;
   extern __shared__ uint32_t smem[];
@@ -297,17 +323,37 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     // Prefixes are dealt to the parts of a sharded search in blocks of kDeal consecutive prefixes
     // (part p owns blocks p, p + nparts, ...), independently of the batch size, which is a power
     // of two <= kDeal so that a batch never straddles two blocks.
-    const uint64_t lt = b * (uint64_t)batch;
-    const uint64_t t_first = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
+    // The first chunk_tickets tickets (search_5lut on large states) are (prefix, chunk of 32 pairs)
+    // items over the first prefixes made of allowed gates only, as in k_filter7_pm: on a dense
+    // state the tuples in front of the first match are then decomposed by many warps, not one.
+    const bool chunked = b < chunk_tickets;
+    const uint64_t lt = chunked ? b : (b - chunk_tickets) * (uint64_t)batch;
+    const uint64_t dealt = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
         + (lt % kDeal);
-    if (t_first >= total) break;
-    if (P == 3 && t_first > stop_at) break;
-    if (ahead) fetch();
-    const uint64_t t_end = min(t_first + (uint64_t)batch, total);
-
+    uint64_t t_first, t_end;
+    uint32_t q_begin = 0, q_limit = 0xffffffffu;
     int pre[P];
     uint64_t base_rank;
-    unrank_prefix<P, K>(t_first, n, pre, base_rank);
+    if (chunked) {
+      if (dealt >= chunk_items) {   // the last deal block is shorter for some parts
+        if (ahead) fetch();
+        continue;
+      }
+      q_begin = (uint32_t)(dealt % (uint64_t)chunks_per_prefix) * 32u;
+      q_limit = q_begin + 32u;
+      if (ahead) fetch();
+      chunk_ticket_prefix<P, K>(dealt / (uint64_t)chunks_per_prefix, n, inmask, pre, t_first,
+          base_rank);
+      t_end = t_first + 1;
+      if (P == 3 && t_first > stop_at) break;
+    } else {
+      t_first = t_offset + dealt;
+      if (t_first >= total) break;
+      if (P == 3 && t_first > stop_at) break;
+      if (ahead) fetch();
+      t_end = min(t_first + (uint64_t)batch, total);
+      unrank_prefix<P, K>(t_first, n, pre, base_rank);
+    }
    for (uint64_t gt = t_first; gt < t_end && !warp_finished; gt++) {
     if (gt != t_first) {
       // successor of the prefix among the P-subsets of {0..n-3}; the combinations sharing the
@@ -322,7 +368,8 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     const int last = pre[P - 1];
     const int r = n - last - 1;
     const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
-    swept_local += Q;
+    if (q_begin >= max(Q, 1u)) continue;   // chunk ticket beyond this prefix's pairs
+    if (q_begin == 0) swept_local += Q;
     bool rejected = false;
 #pragma unroll
     for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
@@ -364,7 +411,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
 
     bool warp_done = false;
     unsigned long long emitted = 0;
-    for (uint32_t q0 = 0; q0 < Q && !warp_done; q0 += 32) {
+    for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !warp_done; q0 += 32) {
       const uint32_t q = q0 + lane;
       bool alive = q < Q;
       int pi, pj;

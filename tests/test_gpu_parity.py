@@ -256,8 +256,10 @@ def test_chunked_and_prefix_forms_agree():
         "    eng.load(S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed])\n"
         "    whole = eng.filter7_part(0, 1)\n"
         "    parts = np.sort(np.concatenate([eng.filter7_part(p, 3) for p in range(3)]))[:100000]\n"
+        "    r5 = sb.search_5lut(eng, S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed],\n"
+        "                        sb.Xorshift1024(np.random.RandomState(n).bytes(128)))\n"
         "    out.append([len(whole), hashlib.sha1(whole.tobytes()).hexdigest(), hashlib.sha1(parts.tobytes()).hexdigest(),\n"
-        "                whole[:2000].tolist() if n == 130 and fixed[0][0] == 1 else []])\n"
+        "                whole[:2000].tolist() if n == 130 and fixed[0][0] == 1 else [], [int(r5.found)] + [int(x) for x in r5.ret]])\n"
         "print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
     outs = {}
     for mode in ("0", "1", "2"):
@@ -273,6 +275,14 @@ def test_chunked_and_prefix_forms_agree():
     want, _ = S.oracle_filter7(S.synthetic_state(n, seed=n), S.sbox_target(S.rijndael_sbox(), n % 8),
                                S.mux_mask(fixed), [b for b, _ in fixed], cap=2000)
     assert [sb.lut.unpack_tuple7(p) for p in outs["1"][3][3]] == want.tolist()
+    # search_5lut on the same states (n = 130: fused kernel, with and without its chunked head)
+    # against the oracle where that is quick (dense states: an early match)
+    for idx, (n, fixed) in ((3, (130, [(1, 1), (2, 0), (4, 1), (7, 1)])),):
+        o_rng = S.OrcRng.from_seed(np.random.RandomState(n).bytes(128))
+        found, ret, _ = S.oracle_search(5, S.synthetic_state(n, seed=n),
+                                        S.sbox_target(S.rijndael_sbox(), n % 8), S.mux_mask(fixed),
+                                        [b for b, _ in fixed], o_rng)
+        assert outs["1"][idx][4] == [int(found)] + [int(x) for x in ret]
 
 
 def _max_size_case():
