@@ -149,8 +149,7 @@ struct sbg_handle {
   DevCtl *h_ctl_out = nullptr;   // pinned: control words read back
   uint64_t *h_head = nullptr;    // pinned: first kHeadEntries of the sorted list, read back with them
   DevTables *d_tab = nullptr;    // lane-indexed ordering tables
-  uint8_t *d_pos5 = nullptr;
-  uint8_t *h_pos5 = nullptr;     // pinned
+  uint8_t *d_pos5 = nullptr;     // written by k_begin5 from its argument
 
   uint64_t *d_hits = nullptr;    // unordered feasible tuples of this device
   char *d_sorted_block = nullptr;  // [control words, 128 B][sorted list]
@@ -653,9 +652,6 @@ void build_params7(sbg_handle *h, const uint8_t *outer_order, const uint8_t *mid
   }
 }
 
-// Bytes of the per-call block that travel host -> device: control words + the two position tables
-// (DevParams7::minpos3 is built on the device by k_prepare7).
-constexpr size_t kCallUploadBytes = offsetof(sbg_handle::DevCall, par) + offsetof(DevParams7, minpos3);
 
 // h->h_par7 holds the two inverse permutations (build_params7); they go to the device as kernel
 // arguments.  reset: also reset the control words (first kernel of a call).
@@ -921,7 +917,6 @@ int sbg_create(sbg_handle **out, int device) {
   SBG_CUDA(h, cudaMallocHost(&h->h_ctl_out, kCtlHeaderBytes + kHeadEntries * sizeof(uint64_t)));
   h->h_head = reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(h->h_ctl_out) + kCtlHeaderBytes);
   SBG_CUDA(h, cudaMalloc(&h->d_pos5, 256));
-  SBG_CUDA(h, cudaMallocHost(&h->h_pos5, 256));
   stamp("small buffers + pinned");
   if (getenv("SBG_BATCH") != nullptr) h->opt_batch = atoi(getenv("SBG_BATCH"));
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
@@ -956,7 +951,7 @@ void sbg_destroy(sbg_handle *h) {
     cudaFree(h->d_slots); cudaFreeHost(h->h_prob);
     cudaFree(h->d_call); cudaFreeHost(h->h_call);
     cudaFreeHost(h->h_ctl_out);
-    cudaFree(h->d_pos5); cudaFreeHost(h->h_pos5);
+    cudaFree(h->d_pos5);
     cudaFree(h->d_tab);
     cudaFree(h->d_hits); cudaFree(h->d_sorted_block); cudaFree(h->d_cub);
     for (int i = 0; i < 8; i++) cudaEventDestroy(h->ev[i]);
