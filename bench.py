@@ -490,9 +490,10 @@ def main():
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "traffic": dram_per_launch,
                 "note": "algorithmic bytes = 224 B per 7-combination (SURVEY.md 8d); operands are "
-                        "served from shared memory, compulsory DRAM traffic is the 33 KB problem block "
-                        "per launch, so frac > 1 is expected; the binding resource is integer-ALU issue "
-                        "(76 % of that pipe's peak, ncu), see profiles/ and DESIGN.md",
+                        "served from shared memory, compulsory DRAM traffic is the problem block (31-50 KB "
+                        "per launch, ncu), so frac > 1 is expected; the binding resource is integer-ALU "
+                        "issue (57-71 % of that pipe's measured peak, ncu capture F), see profiles/ and "
+                        "DESIGN.md",
             },
             "clocks": clocks,
         }
