@@ -129,6 +129,17 @@ int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
     const uint8_t *middle_order, sbg_result *res);
 
 /* ---- helpers shared with the host side ------------------------------------------------------ */
+/* Test hook, no device needed: how a sweep's work is cut into tickets ("Dense
+   states").  width = 7 with prefix_gates = 4 or 5 (search_7lut phase 1), width = 5 with
+   prefix_gates = 3 (search_5lut, fused kernel); n >= 8 gates, `excluded` = bit g set for an excluded
+   gate g < 8 (lut.c:177-185); mode 0 = whole-prefix tickets only, 1 = a head of `waves` waves of
+   (prefix, chunk) tickets over the allowed gates, 2 = chunk tickets throughout.
+   out[0] = chunk tickets' items, out[1] = chunks per prefix, out[2] = lexicographic rank, among all
+   prefixes, of the first prefix left to the whole-prefix tickets (= out[3] if none is left),
+   out[3] = number of prefixes. */
+int sbg_plan_tickets(int width, int prefix_gates, int n, uint32_t excluded, int mode,
+                     uint64_t waves, uint64_t *out);
+
 /* Row k of the ordering tables (lut.c:189-229 for width 5, lut.c:396-415 for width 7). */
 int sbg_ordering_row(int width, int k, int *row);
 /* Closed form of get_lut_function without the random fill (lut.c:79-103): returns 1 and the

@@ -327,10 +327,9 @@ struct ChunkPlan {
 // K = size of the combinations, P = gates per prefix, mode: 0 none, 1 a head of `waves` waves of chunk
 // tickets, 2 everything in chunk tickets.
 template <int P, int K>
-ChunkPlan plan_chunks_mode(const sbg_handle *h, int mode, uint64_t waves, uint64_t qmax) {
+ChunkPlan plan_chunks_mode(int n, uint32_t inmask, int mode, uint64_t waves, uint64_t qmax) {
   ChunkPlan pl;
-  const int n = h->n;
-  const int na = n - __builtin_popcount(h->inmask & 0xffu);   // allowed gates
+  const int na = n - __builtin_popcount(inmask & 0xffu);   // allowed gates
   const uint64_t total_c = na >= K ? h_binom[na - (K - P)][P] : 0;
   if (mode == 0 || total_c == 0) return pl;
   // qmax = lane items of the first (largest) prefix
@@ -359,7 +358,7 @@ ChunkPlan plan_chunks_mode(const sbg_handle *h, int mode, uint64_t waves, uint64
     }
     for (int i = 0; i < P; i++) {
       int g = c[i];
-      for (int bit = 0; bit < 8; bit++) g += (((h->inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
+      for (int bit = 0; bit < 8; bit++) g += (((inmask >> bit) & 1u) != 0 && bit <= g) ? 1 : 0;
       c[i] = g;
     }
     const int nr = n - (K - P);
@@ -384,7 +383,7 @@ int launch_sweep(sbg_handle *h, int part, int nparts, int max_warps, bool emit5 
   // machine instead of being decomposed by the one warp that owns their prefix
   ChunkPlan pl;
   if (P == 3 && !emit5 && max_warps == 0 && h->opt_head != 0 && n >= kHeadAlwaysMinGates) {
-    pl = plan_chunks_mode<P, P + 2>(h, 1, kHeadWaves5, h_binom[n - 3][2]);
+    pl = plan_chunks_mode<P, P + 2>(n, h->inmask, 1, kHeadWaves5, h_binom[n - 3][2]);
   }
   const uint64_t tickets = pl.all ? 0 : (total - pl.t_offset + nparts - 1) / nparts;
   const uint64_t chunk_tickets = (pl.items + kDeal * nparts - 1) / (kDeal * nparts) * kDeal;
@@ -436,7 +435,7 @@ ChunkPlan plan_chunks(const sbg_handle *h, int m, bool retry) {
   if (retry) mode = n >= kHeadAlwaysMinGates ? 2 : 0;
   // lane items: (e,f) pairs out of the n-5 gates that leave room for g; single f for 5-gate prefixes
   const uint64_t qmax = P == 4 ? h_binom[n - 5][2] : (uint64_t)(n - 6);
-  return plan_chunks_mode<P, 7>(h, mode,
+  return plan_chunks_mode<P, 7>(n, h->inmask, mode,
       h->opt_head_waves > 0 ? (uint64_t)h->opt_head_waves : kHeadWaves, qmax);
 }
 
@@ -748,6 +747,31 @@ bool valid_order(const uint8_t *order) {
 // ---- C ABI -------------------------------------------------------------------------------------
 
 extern "C" {
+
+int sbg_plan_tickets(int width, int prefix_gates, int n, uint32_t excluded, int mode,
+    uint64_t waves, uint64_t *out) {
+  build_host_tables();
+  if (out == nullptr || n < width || n > SBG_MAX_GATES) return SBG_ERR_ARG;
+  ChunkPlan pl;
+  uint64_t total = 0;
+  if (width == 7 && prefix_gates == 4 && n >= 8) {
+    pl = plan_chunks_mode<4, 7>(n, excluded, mode, waves, h_binom[n - 5][2]);
+    total = h_binom[n - 3][4];
+  } else if (width == 7 && prefix_gates == 5 && n >= 8) {
+    pl = plan_chunks_mode<5, 7>(n, excluded, mode, waves, (uint64_t)(n - 6));
+    total = h_binom[n - 2][5];
+  } else if (width == 5 && prefix_gates == 3 && n >= 8) {
+    pl = plan_chunks_mode<3, 5>(n, excluded, mode, waves, h_binom[n - 3][2]);
+    total = h_binom[n - 2][3];
+  } else {
+    return SBG_ERR_ARG;
+  }
+  out[0] = pl.items;
+  out[1] = (uint64_t)pl.chunks;
+  out[2] = pl.items == 0 ? 0 : (pl.all ? total : pl.t_offset);
+  out[3] = total;
+  return SBG_OK;
+}
 
 int sbg_ordering_row(int width, int k, int *row) {
   build_host_tables();

@@ -39,6 +39,8 @@ SIGNATURES = {
     "sbg_last_error": (C.c_char_p, [C.c_void_p]),
     "sbg_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sbg_launch_count": (C.c_uint64, [C.c_void_p]),
+    "sbg_plan_tickets": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint64,
+                                   C.POINTER(C.c_uint64)]),
     "sbg_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_int]),
     "sbg_load_problem": (C.c_int, [C.c_void_p, u64p, C.c_int, u64p, u64p, i8p]),
     "sbg_stage_problem": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_int, u64p, u64p, i8p]),

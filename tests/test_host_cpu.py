@@ -73,3 +73,56 @@ def test_engine_fails_loudly_without_gpu():
 def test_missing_library_is_an_error(tmp_path):
     with pytest.raises(sb.NativeLibraryError):
         native.load_library(str(tmp_path / "nope.so"))
+
+
+def test_ticket_plan_covers_the_allowed_prefixes_in_order():
+    """sbg_plan_tickets (host planning code of the product, no device needed): the chunk tickets
+    cover the lexicographically first prefixes made of allowed gates, and the whole-prefix tickets
+    start at the rank -- among ALL prefixes -- of the first allowed prefix that is not covered."""
+    import ctypes as C
+    import itertools
+    from math import comb
+    lib = native.load_library()
+    out = (C.c_uint64 * 4)()
+    cases = [(7, 4, 30, 0b00101001, 1, 1), (7, 4, 30, 0, 1, 1), (7, 4, 26, 0b11, 1, 2),
+             (7, 5, 24, 0b1001, 1, 1), (5, 3, 40, 0b01000101, 1, 1), (5, 3, 36, 0, 1, 1),
+             (7, 4, 20, 0b101, 2, 1), (7, 4, 20, 0b101, 0, 1), (7, 4, 12, 0xff, 1, 1)]
+    for width, pg, n, excluded, mode, waves in cases:
+        assert lib.sbg_plan_tickets(width, pg, n, excluded, mode, waves, out) == 0
+        items, chunks, t_offset, total = (int(x) for x in out)
+        universe = n - (width - pg)                      # prefixes are pg-subsets of the first gates
+        assert total == comb(universe, pg)
+        if mode == 0:
+            assert (items, t_offset) == (0, 0)
+            continue
+        allowed_gates = [g for g in range(universe) if not (g < 8 and (excluded >> g) & 1)]
+        if n - bin(excluded & 0xff).count("1") < width:      # no combination of allowed gates at all
+            assert items == 0
+            continue
+        qmax = comb(n - pg - 1, 2) if (width, pg) == (7, 4) else \
+            (n - 6 if (width, pg) == (7, 5) else comb(n - 3, 2))
+        assert chunks == max(1, (qmax + 31) // 32)
+        assert items % chunks == 0
+        covered = items // chunks
+        n_allowed = comb(len(allowed_gates), pg)
+        if n_allowed == 0:
+            assert items == 0
+            continue
+        want_cover = n_allowed if mode == 2 else min(n_allowed, max(1, waves * 2368 // chunks))
+        assert covered == want_cover
+        # rank of the first uncovered allowed prefix among all prefixes (lexicographic order)
+        if covered == n_allowed:
+            assert t_offset == total
+        else:
+            first_left = next(itertools.islice(itertools.combinations(allowed_gates, pg), covered, None))
+            rank = 0
+            prev = -1
+            for pos, g in enumerate(first_left):
+                for y in range(prev + 1, g):
+                    rank += comb(universe - y - 1, pg - pos - 1)
+                prev = g
+            assert t_offset == rank
+            # everything below that rank is either covered or contains an excluded gate
+            below = list(itertools.islice(itertools.combinations(range(universe), pg), rank))
+            assert sum(1 for c in below if all(g in allowed_gates for g in c)) == covered
+    assert lib.sbg_plan_tickets(6, 4, 30, 0, 1, 1, out) != 0
