@@ -51,6 +51,7 @@ extern "C" {
 #define SBG_LIST_CAP 100000    /* lut.c:291,316-318: at most this many feasible 7-tuples are tried */
 #define SBG_KEY_NONE UINT64_MAX
 #define SBG_PROBLEM_SLOTS 64    /* device-resident search states per handle */
+#define SBG_LANES 8             /* searches of one sbg_search_batch() call that run concurrently */
 
 typedef struct sbg_handle sbg_handle;
 
@@ -81,16 +82,32 @@ const char *sbg_last_error(const sbg_handle *h);
 /* Run on an externally owned stream (a cudaStream_t, e.g. torch's current stream); NULL restores
    the handle's own stream. */
 int sbg_set_stream(sbg_handle *h, void *cuda_stream);
-/* Number of this library's own kernels the handle has launched so far (bench.py reports it;
-   CUB's radix-sort kernels are not counted). */
+/* Number of kernels the handle has launched so far (all of them this library's own; bench.py
+   reports it). */
 uint64_t sbg_launch_count(const sbg_handle *h);
-/* CUDA-event time (ms) spent in the named kernel family by the last search call:
-   0 = search5, 1 = filter7, 2 = sort, 3 = decomp7. */
+/* Kernel timing is off by default (an event between two kernels of a chain forbids their
+   overlap); sbg_set_timing(h, 1) or SBG_TIMING=1 turns it on.  sbg_last_kernel_ms() then gives the
+   CUDA-event time (ms) of the named kernel family in the last call (summed over the searches of a
+   batch): 0 = search5, 1 = filter7 (phase 1), 2 = ordering the hit list, 3 = decomp7. */
+int sbg_set_timing(sbg_handle *h, int on);
 float sbg_last_kernel_ms(const sbg_handle *h, int which);
+/* Bytes this handle has shipped so far: out[0] = problem data host->device (gate tables that
+   changed, target, mask; as kernel arguments or copies), out[1] = results device->host (mapped
+   memory and copies), out[2..4] = state changes that took a bulk copy / travelled as kernel
+   arguments / were no change at all. */
+int sbg_transfer_stats(const sbg_handle *h, uint64_t *out /*5*/);
+/* Measures the device's LOP3 issue rate (warp instructions per second, whole chip): the ceiling
+   the search kernels are bound by. */
+int sbg_alu_peak(sbg_handle *h, double *warp_instr_per_s);
 
 /* ---- problem -------------------------------------------------------------------------------- */
-/* Uploads one search state: n gate tables, target, mask, and the -1 terminated list of input-bit
-   gates already used as multiplexer selectors (lut.c:177-185).  Host pointers. */
+/* Makes one search state the current problem: n gate tables, target, mask, and the -1 terminated
+   list of input-bit gates already used as multiplexer selectors (lut.c:177-185).  Host pointers.
+   The gate tables stay resident on the device between calls (the replacement of the `state`
+   array the reference re-broadcasts per call): only the gates that differ from the previous state
+   of the slot are shipped -- a graph build only ever appends gates (state.h:87) or replaces a
+   suffix when it backtracks -- together with target and mask, as arguments of the next search's
+   first kernel; compression to the masked positions happens on the device. */
 int sbg_load_problem(sbg_handle *h, const uint64_t *tables, int n, const uint64_t *target,
     const uint64_t *mask, const int8_t *inbits);
 /* The same in two steps, for callers that keep several search states resident in HBM: stage a
@@ -106,6 +123,39 @@ int sbg_search5(sbg_handle *h, const uint8_t *func_order /*256*/, sbg_result *re
 int sbg_search7(sbg_handle *h, const uint8_t *outer_order /*256*/, const uint8_t *middle_order
     /*256*/, sbg_result *res);
 
+/* ---- one call per node, batches of independent nodes ----------------------------------------- */
+/* A job is what lut_search() does for one node (lut.c:489-631): the 3-LUT scan over the caller's
+   shuffled gate order (lut.c:501-523), search_5lut (lut.c:553) and search_7lut (lut.c:593), each
+   stage only if the earlier ones found nothing -- as ONE launch chain on the device, the stages
+   predicated there, no host round trip in between.  The caller says which stages it wants
+   (lut_search skips search_5lut / search_7lut when the gate budget forbids two / three more gates,
+   lut.c:525-527, 582-586). */
+#define SBG_DO_SCAN3 1
+#define SBG_DO_SEARCH5 2
+#define SBG_DO_SEARCH7 4
+typedef struct {
+  int32_t slot;                /* staged problem (sbg_stage_problem / sbg_load_problem = slot 0) */
+  int32_t flags;               /* SBG_DO_* */
+  const uint8_t *order5;       /* 256: shuffled function order of search_5lut (lut.c:125-135) */
+  const uint8_t *outer7;       /* 256 + 256: the two orders of search_7lut (lut.c:362-378) */
+  const uint8_t *middle7;
+  const uint16_t *gate_order;  /* n: create_circuit's shuffled gate order (sboxgates.c:285-299) */
+} sbg_job;
+typedef struct {
+  int32_t found_stage;         /* 0 nothing, else 3 / 5 / 7 */
+  uint16_t gates3[3];          /* stage 3: LUT inputs in gate_order order (gi, gk, gm) */
+  uint8_t func3, seen3;        /* solved function bits / cells seen under the mask (fill as below) */
+  uint64_t key3;               /* rank of the position triple in gate_order, or SBG_KEY_NONE */
+  sbg_result r5;               /* as sbg_search5 (found = 0 if the stage did not run) */
+  sbg_result r7;               /* as sbg_search7 */
+} sbg_node_result;
+/* One node; returns as soon as a stage has matched. */
+int sbg_search_node(sbg_handle *h, const sbg_job *job, sbg_node_result *result);
+/* Independent nodes (the first children of a create_circuit node, sboxgates.c:458-607; the output
+   bits of generate_graph, sboxgates.c:701-788; the -i iterations): their chains run concurrently
+   on up to SBG_LANES streams, results are read once per job. */
+int sbg_search_batch(sbg_handle *h, int njobs, const sbg_job *jobs, sbg_node_result *results);
+
 /* ---- sharded building blocks (one process per GPU; part = rank, nparts = world size) -------- */
 /* 5-LUT: this part's share of C(n,5); *key = local minimum key or SBG_KEY_NONE. */
 int sbg_search5_part(sbg_handle *h, int part, int nparts, const uint8_t *func_order,
@@ -119,9 +169,17 @@ int sbg_finish5(sbg_handle *h, uint64_t key, const uint8_t *func_order, sbg_resu
    nparts == 1 the device-resident result is installed as the list, so sbg_decomp7_part() may follow
    directly. */
 int sbg_filter7_part(sbg_handle *h, int part, int nparts, uint64_t *list, int *count);
-/* Installs the merged hit list (any order, duplicates not allowed; it is sorted and truncated to
-   SBG_LIST_CAP here, which reproduces lut.c:316-318 for size == 1). */
+/* Installs the merged hit list: `list` is the concatenation of the parts' ascending lists (at most
+   64 ascending runs, no duplicates); the runs are merged on the device and cut at SBG_LIST_CAP,
+   which reproduces lut.c:316-349 for size == 1. */
 int sbg_set_list7(sbg_handle *h, const uint64_t *list, int count);
+/* The same without touching the host: this part's ordered list as a device pointer (valid until the
+   next search on the handle), and the merge of `nruns` ascending runs that already sit in device
+   memory, run r at runs + r * stride with counts[r] entries (what an all-gather of the parts'
+   lists into one buffer gives). */
+int sbg_list7_device(sbg_handle *h, const uint64_t **list, int *count);
+int sbg_set_list7_device(sbg_handle *h, const uint64_t *runs, uint64_t stride, const int *counts,
+    int nruns);
 /* 7-LUT phase 2 over list indices congruent to part modulo nparts. */
 int sbg_decomp7_part(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
     const uint8_t *middle_order, uint64_t *key);

@@ -9,11 +9,12 @@ does not.
 """
 from .rng import Xorshift1024
 from .lut import LutEngine, SearchResult, NO_GATE, search_5lut, search_7lut, shuffled_order, \
-    shuffled_orders7, ordering_row, solve_inner, lut_table
+    shuffled_orders7, ordering_row, solve_inner, lut_table, lut_search, LutSearchResult
 from .native import load_library, NativeLibraryError
 
 __all__ = [
     "Xorshift1024", "LutEngine", "SearchResult", "NO_GATE", "search_5lut", "search_7lut",
     "shuffled_order", "shuffled_orders7", "ordering_row", "solve_inner", "lut_table",
+    "lut_search", "LutSearchResult",
     "load_library", "NativeLibraryError",
 ]

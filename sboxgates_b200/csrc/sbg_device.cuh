@@ -5,7 +5,8 @@
 // (check_n_lut_possible), lut.c:79-109 (get_lut_function), lut.c:116-249 (search_5lut) and
 // lut.c:256-487 (search_7lut); see DESIGN.md for how the loops were restructured.
 //
-// Data layout in HBM (DevProblem, 16.5 KB, uploaded once per search state):
+// Data layout in HBM (DevProblem; the uncompressed tables stay resident, the rest is derived on the
+// device whenever gates, target or mask change):
 //   * tables are compressed to the masked positions only: bit i of a compressed table is the
 //     table's value at the i-th set position of the mask, so a search under a mask of popcount m
 //     touches NW = ceil(m/32) words per table instead of 8 (every test in the reference is
@@ -41,20 +42,45 @@ struct DevProblem {
   // the target's value on every position of a set S" <=> bit g of AND_{p in S} xr[p], and "gate g
   // takes the opposite value on all of S" <=> bit g of ~OR_{p in S} xr[p].
   uint32_t xr[256][16];
+  // The device-resident copy of the state's gate tables (state.h:72-88, 256 bits per gate,
+  // gate-major) with the target and mask they were last compressed under.  A call ships only the
+  // gates that differ from what is here (kernel arguments, or one copy for a large change); tabs,
+  // T, M and xr above are derived from it on the device (prepare_problem).
+  uint32_t full[kMaxGatesPad][8];
+  uint32_t target_full[8];
+  uint32_t mask_full[8];
 };
 
 struct DevCtl {
   unsigned long long ticket;       // next work item
-  unsigned long long best;         // minimum key found so far
+  unsigned long long best;         // minimum key found so far by the running stage
   unsigned long long stop_ticket;  // search5: tickets above this cannot improve `best`
-  unsigned long long hit_count;    // filter7: feasible tuples appended
+  unsigned long long hit_count;    // filter7 / two-kernel search5: slots reserved in the hit buffer
   unsigned long long swept;        // tuples put through the feasibility test
   unsigned long long feasible;     // search5: feasible tuples met
-  unsigned long long ticket2;      // decomp7: next list entry (phase 2 runs after phase 1 without a reset)
-  unsigned int overflow;           // filter7: hit buffer too small
-  unsigned int list_count;         // written by k_sort_small: entries of the sorted list
-  unsigned int sorted_ok;          // 1 if k_sort_small produced the sorted list on the device
+  unsigned long long ticket2;      // decomp5 / decomp7: next list entry
+  unsigned long long seq;          // sequence number of the call (echoed to the host with each result)
+  unsigned int overflow;           // 1: hit buffer too small, 2: ticket table too small
+  unsigned int list_count;         // written by k_offsets: entries of the ordered list (<= cap)
+  unsigned int ctas_done;          // last-CTA detection of the stage-closing kernels
+  unsigned int stage_found;        // 0, or 3 / 5 once that stage matched (0xff: a stage was left
+                                   // incomplete): later stages of the chain return at once
+  unsigned int skip5, skip7;       // stages not asked for (node calls)
+};
+
+// What the device tells the host, in MAPPED PINNED host memory, one block per lane: the last CTA of
+// a stage's closing kernel stores the stage's numbers, fences system-wide, then stores the call's
+// sequence number into seq[stage]; the host spins on that word -- no copy, no stream
+// synchronisation.  Stages: 0 = 3-LUT scan (lut.c:501-523), 1 = search_5lut, 2 = search_7lut.
+struct HostOut {
+  unsigned long long key[3];
+  unsigned long long swept[3];
+  unsigned long long feasible[3];   // stage 1: feasible 5-tuples met; stage 2: list length
+  unsigned long long tuple;         // stage 2: the winning list entry ...
+  unsigned long long tuple_prev;    // ... and the one before it (stale-cache quirk, lut.c:432-435)
+  unsigned int overflow[3];
   unsigned int pad;
+  unsigned long long seq[3];
 };
 
 // Per-call parameters of the 7-LUT decomposition.  The host supplies where each function sits in
@@ -74,6 +100,11 @@ struct DevParams7 {
 struct DevTables {
   uint8_t src5[10][32];    // search5: ordering k, lane (u,v2) -> canonical cell
   uint32_t src7[25][32];   // decomp7: outer triple j, lane (u0,v4) -> 4 cells (u2,u1)
+  // k_begin: the 6,561 entries of DevParams7::minpos3 listed by number of unconstrained bits
+  // (level l = entries m3_level[l] .. m3_level[l+1]-1); info = entry | (level 0: the function,
+  // else: 3^j of its lowest unconstrained bit j) << 16
+  uint32_t m3_info[6561];
+  int32_t m3_level[10];
 };
 
 __constant__ uint64_t c_binom[501][8];   // C(m, r), 0 <= m <= 500, 0 <= r <= 7
@@ -161,8 +192,71 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t saddr) {
   return v;
 }
 
-__device__ __forceinline__ uint64_t volatile_load(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long volatile_load(const unsigned long long *p) {
   return *reinterpret_cast<const volatile unsigned long long *>(p);
+}
+
+__device__ __forceinline__ uint32_t volatile_load32(const unsigned int *p) {
+  return *reinterpret_cast<const volatile unsigned int *>(p);
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialisation
+// attribute starts while its predecessor in the stream is still draining; everything before this
+// call (staging the problem's tables into shared memory, which no kernel of a chain writes) overlaps
+// the predecessor's tail, everything after it sees the predecessor's memory.  Without the attribute
+// both calls are no-ops.
+__device__ __forceinline__ void wait_for_predecessor() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void let_successor_start() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// End of a stage-closing kernel.  Every CTA calls it (no early returns in those kernels); exactly one
+// -- the last to arrive -- gets `true`, with every other CTA's global writes visible to it.
+__device__ __forceinline__ bool last_cta_of_grid(DevCtl *ctl) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ctl->ctas_done, 1u);
+    s_last = prev == gridDim.x - 1;
+    if (s_last) {
+      ctl->ctas_done = 0;   // the next kernel of the chain counts from zero
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  return s_last != 0;
+}
+
+// The closing CTA's thread 0: stage results -> mapped host memory, sequence number last; then the
+// control words the stages share are made ready for the next stage of the chain (its kernels cannot
+// pass their wait_for_predecessor() / stream order before this kernel has completed).
+__device__ __forceinline__ void close_stage(DevCtl *ctl, HostOut *out, int stage,
+    unsigned long long key, unsigned long long feasible, unsigned long long tuple,
+    unsigned long long tuple_prev) {
+  const unsigned int overflow = volatile_load32(&ctl->overflow);
+  out->key[stage] = key;
+  out->swept[stage] = volatile_load(&ctl->swept);
+  out->feasible[stage] = feasible;
+  out->overflow[stage] = overflow;
+  if (stage == 2) {
+    out->tuple = tuple;
+    out->tuple_prev = tuple_prev;
+  }
+  if (key != ~0ull) ctl->stage_found = 3 + 2 * stage;      // later stages of the chain return at once
+  else if (overflow != 0) ctl->stage_found = 0xffu;        // incomplete stage: the host redoes it
+  ctl->ticket = 0;
+  ctl->ticket2 = 0;
+  ctl->hit_count = 0;
+  ctl->swept = 0;
+  ctl->feasible = 0;
+  ctl->best = ~0ull;
+  ctl->stop_ticket = ~0ull;
+  ctl->overflow = 0;
+  __threadfence_system();
+  *reinterpret_cast<volatile unsigned long long *>(&out->seq[stage]) = ctl->seq;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -226,16 +320,15 @@ __device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int np
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sweep kernel.  One warp per P-element prefix; lanes take the (f,g) pairs that complete it.
-//   P = 3 (K = 5): search_5lut's loop over C(n,5) (lut.c:174-245), feasibility test and the
-//                  10 x 256 decomposition attempts fused; result = minimum key in ctl->best.
-//   P = 5 (K = 7): phase 1 of search_7lut (lut.c:294-327); result = unordered list of feasible
-//                  combinations (packed 9 bits per gate), sorted afterwards.
+// Sweep kernel of search_5lut.  One warp per 3-gate prefix; lanes take the (d,e) pairs that complete
+// it: search_5lut's loop over C(n,5) (lut.c:174-245), either with the 10 x 256 decomposition
+// attempts fused (large searches; result = minimum key in ctl->best) or only recording the feasible
+// tuples for k_decomp5 (small ones).
 //
-// Feasibility (lut.c:34-66) of prefix + (f,g): no cell of the 2^K-cell partition may hold both a
+// Feasibility (lut.c:34-66) of prefix + (d,e): no cell of the 32-cell partition may hold both a
 // masked 1 and a masked 0 of the target.  A prefix cell that is already pure stays pure however it
 // is split, so only the "mixed" prefix cells are kept (their ones C1 = C & T and zeros C0 = C & ~T,
-// in shared memory); each must be split by f and g into four parts none of which meets both C1 and
+// in shared memory); each must be split by d and e into four parts none of which meets both C1 and
 // C0.  A pair is dropped at the first cell it fails on.
 // Chunk tickets (see k_sweep / k_filter7_pm): the t-th P-gate prefix made of allowed gates only, as
 // gate numbers, with its rank among all prefixes (for the stop rule) and the rank of its first
@@ -261,18 +354,18 @@ __device__ __noinline__ void chunk_ticket_prefix(uint64_t t, int n, uint32_t inm
   }
 }
 
-template <int NW, int P>
+// closes = this launch ends the search_5lut stage (fused form): its last CTA publishes the result.
+template <int NW>
 __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, uint64_t *__restrict__ hits,
-    unsigned long long hits_cap, int part, int nparts, unsigned long long list_cap,
-    int batch, int max_warps, bool emit5, const DevTables *__restrict__ tab,
-    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix,
-    unsigned long long chunk_tickets) {
-  constexpr int K = P + 2;
-  constexpr int NC = 1 << P;
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const uint8_t *__restrict__ pos_of,
+    uint64_t *__restrict__ hits, unsigned long long hits_cap, int part, int nparts, int batch,
+    bool emit5, const DevTables *__restrict__ tab, unsigned long long t_offset,
+    unsigned long long chunk_items, int chunks_per_prefix, unsigned long long chunk_tickets) {
+  constexpr int P = 3, K = 5, NC = 1 << P;
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_pos[256];
 
+  wait_for_predecessor();   // the chain's first kernel derives the problem block
   const int n = prob->n;
   const int npad = (n + 3) & ~3;
   uint32_t *s_tabs = smem;
@@ -280,12 +373,11 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   const int warp = threadIdx.x >> 5;
   uint32_t *cells = smem + NW * npad + warp * (NC * 2 * NW);  // per mixed cell: C1[NW], C0[NW]
 
-  if constexpr (P == 3) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
-  }
   stage_tables(s_tabs, prob, NW, npad);
-  // overflow retry: only the first max_warps warps work (bounds the hits in flight)
-  if (max_warps > 0 && (int)(blockIdx.x * kWarpsPerCta + warp) >= max_warps) return;
+  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip5) != 0;
+  if (!skip) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
+  __syncthreads();
 
   uint32_t T[NW], M[NW];
 #pragma unroll
@@ -304,22 +396,15 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   unsigned long long next_b = 0, next_stop = ~0ull;
   auto fetch = [&]() {
     if (lane == 0) {
-      bool stop = false;
-      if (P == 5) stop = volatile_load(&ctl->hit_count) >= list_cap;
-      if (P == 3) next_stop = volatile_load(&ctl->stop_ticket);
-      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+      next_stop = volatile_load(&ctl->stop_ticket);
+      next_b = atomicAdd(&ctl->ticket, 1ull);
     }
   };
-  // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
-  // would be worked on even if the cap was reached meanwhile, doubling the hits in flight.
-  const bool ahead = max_warps == 0;
-  if (ahead) fetch();
+  fetch();
   bool warp_finished = false;
   while (!warp_finished) {
-    if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     const unsigned long long stop_at = __shfl_sync(kFull, next_stop, 0);
-    if (b == ~0ull) break;
     // Prefixes are dealt to the parts of a sharded search in blocks of kDeal consecutive prefixes
     // (part p owns blocks p, p + nparts, ...), independently of the batch size, which is a power
     // of two <= kDeal so that a batch never straddles two blocks.
@@ -336,21 +421,21 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     uint64_t base_rank;
     if (chunked) {
       if (dealt >= chunk_items) {   // the last deal block is shorter for some parts
-        if (ahead) fetch();
+        fetch();
         continue;
       }
       q_begin = (uint32_t)(dealt % (uint64_t)chunks_per_prefix) * 32u;
       q_limit = q_begin + 32u;
-      if (ahead) fetch();
+      fetch();
       chunk_ticket_prefix<P, K>(dealt / (uint64_t)chunks_per_prefix, n, inmask, pre, t_first,
           base_rank);
       t_end = t_first + 1;
-      if (P == 3 && t_first > stop_at) break;
+      if (t_first > stop_at) break;
     } else {
       t_first = t_offset + dealt;
       if (t_first >= total) break;
-      if (P == 3 && t_first > stop_at) break;
-      if (ahead) fetch();
+      if (t_first > stop_at) break;
+      fetch();
       t_end = min(t_first + (uint64_t)batch, total);
       unrank_prefix<P, K>(t_first, n, pre, base_rank);
     }
@@ -369,7 +454,8 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     const int r = n - last - 1;
     const uint32_t Q = (uint32_t)(r * (r - 1) / 2);
     if (q_begin >= max(Q, 1u)) continue;   // chunk ticket beyond this prefix's pairs
-    if (q_begin == 0) swept_local += Q;
+    // T-units (lut.c:174-187): the combinations of the pair chunks this ticket goes through
+    swept_local += (uint64_t)(min(Q, q_limit) - q_begin);
     bool rejected = false;
 #pragma unroll
     for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
@@ -410,7 +496,6 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     const int mc = __popc(mixed_ballot);
 
     bool warp_done = false;
-    unsigned long long emitted = 0;
     for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !warp_done; q0 += 32) {
       const uint32_t q = q0 + lane;
       bool alive = q < Q;
@@ -421,7 +506,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       if ((gf < 8 && ((inmask >> gf) & 1u)) || (gg < 8 && ((inmask >> gg) & 1u))) alive = false;
 
       if (mc > 0) {
-        uint32_t m11[NW], m10[NW], m01[NW], m00[NW];  // the four (f,g) minterms
+        uint32_t m11[NW], m10[NW], m01[NW], m00[NW];  // the four (d,e) minterms
 #pragma unroll
         for (int w = 0; w < NW; w++) {
           const uint32_t tf = s_tabs[w * npad + gf];
@@ -453,7 +538,10 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       uint32_t fb = __ballot_sync(kFull, alive);
       if (fb == 0) continue;
 
-      if constexpr (P == 5) {
+      if (emit5) {
+        // Two-kernel form for small searches: feasible 5-tuples are only recorded here (rank and
+        // packed gates) and decomposed by k_decomp5, one warp per tuple, so that a warp meeting
+        // several of them does not become the kernel's critical path.
         const int cnt = __popc(fb);
         unsigned long long base_slot = 0;
         if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)cnt);
@@ -462,114 +550,103 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
           const unsigned long long slot = base_slot + __popc(fb & lanemask_lt());
           uint64_t packed = 0;
 #pragma unroll
-          for (int i = 0; i < P; i++) packed = (packed << 9) | (uint64_t)pre[i];
+          for (int i = 0; i < 3; i++) packed = (packed << 9) | (uint64_t)pre[i];
           packed = (packed << 18) | ((uint64_t)gf << 9) | (uint64_t)gg;
-          if (slot < hits_cap) {
-            hits[slot] = packed;
+          if (2 * slot + 1 < hits_cap) {
+            hits[2 * slot] = base_rank + q;
+            hits[2 * slot + 1] = packed;
           } else {
             atomicExch(&ctl->overflow, 1u);
           }
         }
-        // A single prefix never needs to contribute more than the list cap (lut.c:316-318).
-        emitted += cnt;
-        if (emitted >= list_cap) warp_done = true;
-      } else {
-        if (emit5) {
-          // Two-kernel form for small searches: feasible 5-tuples are only recorded here (rank and
-          // packed gates) and decomposed by k_decomp5, one warp per tuple, so that a warp meeting
-          // several of them does not become the kernel's critical path.
-          const int cnt = __popc(fb);
-          unsigned long long base_slot = 0;
-          if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)cnt);
-          base_slot = __shfl_sync(kFull, base_slot, 0);
-          if (alive) {
-            const unsigned long long slot = base_slot + __popc(fb & lanemask_lt());
-            uint64_t packed = 0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) packed = (packed << 9) | (uint64_t)pre[i];
-            packed = (packed << 18) | ((uint64_t)gf << 9) | (uint64_t)gg;
-            if (2 * slot + 1 < hits_cap) {
-              hits[2 * slot] = base_rank + q;
-              hits[2 * slot + 1] = packed;
-            } else {
-              atomicExch(&ctl->overflow, 1u);
-            }
+        continue;
+      }
+      // search_5lut: try the 10 orderings x 256 outer functions on each feasible tuple
+      // (lut.c:189-230), here, one after the other -- unless a match in an earlier prefix is
+      // already known (dense states: every warp of the first wave sits on feasible tuples).
+      {
+        unsigned long long st = 0;
+        if (lane == 0) st = volatile_load(&ctl->stop_ticket);
+        if (gt > __shfl_sync(kFull, st, 0)) warp_done = true;
+      }
+      while (fb != 0 && !warp_done) {
+        const int src = __ffs(fb) - 1;
+        fb &= fb - 1;
+        int g5[5];
+        g5[0] = pre[0];
+        g5[1] = pre[1];
+        g5[2] = pre[2];
+        g5[3] = __shfl_sync(kFull, gf, src);
+        g5[4] = __shfl_sync(kFull, gg, src);
+        if (lane == 0) atomicAdd(&ctl->feasible, 1ull);
+        const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
+        if (hit != 0xffffffffu) {
+          const uint64_t key = ((base_rank + q0 + src) << 12) | (uint64_t)hit;
+          if (lane == 0) {
+            atomicMin(&ctl->best, (unsigned long long)key);
+            atomicMin(&ctl->stop_ticket, (unsigned long long)gt);
           }
-          continue;
-        }
-        // search_5lut: try the 10 orderings x 256 outer functions on each feasible tuple
-        // (lut.c:189-230), here, one after the other -- unless a match in an earlier prefix is
-        // already known (dense states: every warp of the first wave sits on feasible tuples).
-        {
-          unsigned long long st = 0;
-          if (lane == 0) st = volatile_load(&ctl->stop_ticket);
-          if (gt > __shfl_sync(kFull, st, 0)) warp_done = true;
-        }
-        while (fb != 0 && !warp_done) {
-          const int src = __ffs(fb) - 1;
-          fb &= fb - 1;
-          int g5[5];
-          g5[0] = pre[0];
-          g5[1] = pre[1];
-          g5[2] = pre[P > 2 ? 2 : 0];
-          g5[3] = __shfl_sync(kFull, gf, src);
-          g5[4] = __shfl_sync(kFull, gg, src);
-          if (lane == 0) atomicAdd(&ctl->feasible, 1ull);
-          const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
-          if (hit != 0xffffffffu) {
-            const uint64_t key = ((base_rank + q0 + src) << 12) | (uint64_t)hit;
-            if (lane == 0) {
-              atomicMin(&ctl->best, (unsigned long long)key);
-              atomicMin(&ctl->stop_ticket, (unsigned long long)gt);
-            }
-            warp_done = true;
-          }
+          warp_done = true;
         }
       }
     }
-    if (P == 3 && warp_done) warp_finished = true;  // every later prefix has a larger key
+    if (warp_done) warp_finished = true;  // every later prefix has a larger key
    }
   }
   if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
+  }  // !skip
+  let_successor_start();
+  if (!emit5 && last_cta_of_grid(ctl) && threadIdx.x == 0 && !skip) {
+    close_stage(ctl, out, 1, volatile_load(&ctl->best), volatile_load(&ctl->feasible), 0, 0);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Second kernel of the two-kernel search_5lut: one warp per recorded feasible 5-tuple.
+// Second kernel of the two-kernel search_5lut: one warp per recorded feasible 5-tuple.  Closes the
+// stage: its last CTA publishes the result.
 template <int NW>
 __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, const uint8_t *__restrict__ pos_of, const uint64_t *__restrict__ hits,
-    const DevTables *__restrict__ tab) {
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const uint8_t *__restrict__ pos_of,
+    const uint64_t *__restrict__ hits, const DevTables *__restrict__ tab) {
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_pos[256];
-  const unsigned long long count = ctl->hit_count;
-  if (ctl->overflow != 0 || (unsigned long long)blockIdx.x * kWarpsPerCta >= count) return;
+  wait_for_predecessor();
   const int n = prob->n;
   const int npad = (n + 3) & ~3;
   uint32_t *s_tabs = smem;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
   stage_tables(s_tabs, prob, NW, npad);
-  uint32_t T[NW], M[NW];
+  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip5) != 0;
+  const unsigned long long count = ctl->hit_count;
+  if (!skip && ctl->overflow == 0 && (unsigned long long)blockIdx.x * kWarpsPerCta < count) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
+    __syncthreads();
+    uint32_t T[NW], M[NW];
 #pragma unroll
-  for (int w = 0; w < NW; w++) {
-    T[w] = prob->T[w];
-    M[w] = prob->M[w];
-  }
-  for (;;) {
-    unsigned long long t = 0;
-    if (lane == 0) t = atomicAdd(&ctl->ticket2, 1ull);
-    t = __shfl_sync(kFull, t, 0);
-    if (t >= count) break;
-    const uint64_t rank = hits[2 * t];
-    if ((volatile_load(&ctl->best) >> 12) < rank) continue;  // a smaller combination matched
-    const uint64_t packed = hits[2 * t + 1];
-    int g5[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) g5[i] = (int)((packed >> (9 * (4 - i))) & 0x1ffu);
-    const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
-    if (hit != 0xffffffffu && lane == 0) {
-      atomicMin(&ctl->best, (unsigned long long)((rank << 12) | (uint64_t)hit));
+    for (int w = 0; w < NW; w++) {
+      T[w] = prob->T[w];
+      M[w] = prob->M[w];
     }
+    for (;;) {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(&ctl->ticket2, 1ull);
+      t = __shfl_sync(kFull, t, 0);
+      if (t >= count) break;
+      const uint64_t rank = hits[2 * t];
+      if ((volatile_load(&ctl->best) >> 12) < rank) continue;  // a smaller combination matched
+      const uint64_t packed = hits[2 * t + 1];
+      int g5[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) g5[i] = (int)((packed >> (9 * (4 - i))) & 0x1ffu);
+      const uint32_t hit = decomp5_tuple<NW>(s_tabs, npad, g5, T, M, lane, s_pos, tab);
+      if (hit != 0xffffffffu && lane == 0) {
+        atomicMin(&ctl->best, (unsigned long long)((rank << 12) | (uint64_t)hit));
+      }
+    }
+  }
+  let_successor_start();
+  if (last_cta_of_grid(ctl) && threadIdx.x == 0 && !skip) {
+    close_stage(ctl, out, 1, volatile_load(&ctl->best), count, 0, 0);
   }
 }
 
@@ -601,10 +678,11 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 // prefix and the position loop does half the accumulates.
 template <int NW, int W, int P, bool FS, bool SH = false>
 __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, unsigned long long hits_cap, int part,
-    int nparts, unsigned long long list_cap, int batch, int max_warps,
-    unsigned long long t_offset, unsigned long long chunk_items, int chunks_per_prefix,
-    unsigned long long chunk_tickets) {
+    DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, uint64_t *__restrict__ aux,
+    uint32_t *__restrict__ tcount, uint32_t *__restrict__ gcount, unsigned long long hits_cap,
+    unsigned long long tickets_cap, int part, int nparts, unsigned long long list_cap, int batch,
+    int max_warps, unsigned long long t_offset, unsigned long long chunk_items,
+    int chunks_per_prefix, unsigned long long chunk_tickets, unsigned long long seg_base) {
   constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
   // Work is handed out through one ordered ticket counter, in lexicographic order, under one stop
@@ -618,6 +696,15 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   //  * the rest are batches of whole prefixes from prefix rank t_offset on (the first prefix the
   //    chunk tickets do not cover): less bookkeeping per combination, the form for sweeps that
   //    have to cover everything.
+  //
+  // ORDERED EMISSION.  The reference's list is in lexicographic order for free (lut.c:316-349); here
+  // hits are produced by thousands of warps at once.  Ticket numbers are monotone in lexicographic
+  // order, a ticket is worked on by one warp, and that warp meets the ticket's hits in increasing
+  // order.  So every hit is stored (anywhere: one atomic reserves the slots of a chunk) together
+  // with (ticket b, index j among the ticket's hits), the warp leaves the ticket's hit count in
+  // tcount[b], and the place of the hit in the ordered list is  prefix_sum(tcount)[b] + j  --
+  // k_offsets does the prefix sum, k_scatter the move.  No sort.
+  wait_for_predecessor();   // the chain's first kernel derives the problem block and its rows
   const int n = prob->n;
   const int m = prob->m;
   const int npad = (n + 3) & ~3;
@@ -627,7 +714,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   uint32_t *cells = s_xr + ((m * ngw + 3) & ~3) + warp * (NC * NW);
-  uint32_t *sx = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW) + warp * m;   // SH only
+  // per warp: the surviving-g vectors of one chunk, word-major (vs[word * 32 + lane])
+  uint32_t *vs = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW) + warp * (ngw * 32);
+  uint32_t *sx = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW + ngw * 32) + warp * m;   // SH only
   static_assert(!SH || (W == 1 && P == 4 && FS), "shifted windows: one word, 4-gate prefixes, n <= 63");
   const uint32_t sx_top = (uint32_t)__cvta_generic_to_shared(sx + 31);   // row 31 of word 0
   const uint32_t xr_base = (uint32_t)__cvta_generic_to_shared(s_xr);
@@ -636,8 +725,13 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   // (max_warps is never negative; the arithmetic only hides the constant from constant folding)
   const uint32_t low31 = 0x7fffffffu ^ ((uint32_t)max_warps >> 31);
 
-  for (int i = threadIdx.x; i < m * ngw; i += blockDim.x) {
-    s_xr[i] = prob->xr[i / ngw][i % ngw];
+  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  // position-major rows: 8-byte cp.async chunks, one row per warp at a time (no division); they
+  // complete together with the gate-major tables (stage_tables commits and waits for both)
+  for (int p = warp; p < m; p += kWarpsPerCta) {
+    if (lane < (ngw >> 1)) {
+      __pipeline_memcpy_async(s_xr + p * ngw + 2 * lane, &prob->xr[p][2 * lane], 8);
+    }
   }
   stage_tables(s_tabs, prob, NW, npad);
   // overflow retry: only the first max_warps warps work (bounds the hits in flight)
@@ -651,7 +745,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   }
   const uint32_t inmask = prob->inmask;
   const uint64_t total = c_binom[n - (K - P)][P];
-  unsigned long long swept_local = 0;
+  unsigned long long swept_lane = 0;   // T-units this lane put through the test (summed at the end)
   unsigned long long next_b = 0;
   auto fetch = [&]() {
     if (lane == 0) {
@@ -668,28 +762,38 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
     if (!ahead) fetch();
     const unsigned long long b = __shfl_sync(kFull, next_b, 0);
     if (b == ~0ull) break;
+    if (b >= tickets_cap) {   // the ticket table is too small for this sweep: the host continues it
+      if (lane == 0) atomicMax(&ctl->overflow, 2u);
+      break;
+    }
+    uint32_t tj = 0;          // hits of this ticket so far
     uint64_t t_first, t_end;
     uint32_t q_begin = 0, q_limit = 0xffffffffu;
-    // dealt to the parts of a sharded search in blocks of kDeal consecutive items, see k_sweep
-    const bool chunked = b < chunk_tickets;
-    const uint64_t lt = chunked ? b : (b - chunk_tickets) * (uint64_t)batch;
+    // A sweep whose tickets outnumber the ticket table runs as several launches ("segments"); this
+    // one hands out tickets seg_base, seg_base + 1, ... and indexes its table from zero.
+    // Dealt to the parts of a sharded search in blocks of kDeal consecutive items, see k_sweep.
+    const unsigned long long bg = seg_base + b;
+    const bool chunked = bg < chunk_tickets;
+    const uint64_t lt = chunked ? bg : (bg - chunk_tickets) * (uint64_t)batch;
     const uint64_t dealt = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
         + (lt % kDeal);
+    bool valid = true;
     if (chunked) {
-      if (dealt >= chunk_items) {   // the last deal block is shorter for some parts
-        if (ahead) fetch();
-        continue;
-      }
+      valid = dealt < chunk_items;   // the last deal block is shorter for some parts
       t_first = dealt / (uint64_t)chunks_per_prefix;
       t_end = t_first + 1;
       q_begin = (uint32_t)(dealt % (uint64_t)chunks_per_prefix) * 32u;
       q_limit = q_begin + 32u;
     } else {
       t_first = t_offset + dealt;
-      if (t_first >= total) break;
+      if (t_first >= total) {        // past the end: every later ticket is, too
+        if (lane == 0) tcount[b] = 0;
+        break;
+      }
       t_end = min(t_first + (uint64_t)batch, total);
     }
     if (ahead) fetch();
+    if (valid) {
     int pre[P];
     uint64_t unused_rank;
     unrank_prefix<P, K>(t_first, chunked ? n_allowed : n, pre, unused_rank);
@@ -713,11 +817,14 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
       const int r = n - last - 2;                   // candidates for (e,)f: last+1 .. n-2
       const uint32_t Q = P == 4 ? (uint32_t)(r * (r - 1) / 2) : (uint32_t)r;
       if (q_begin >= max(Q, 1u)) continue;          // head launch: no such chunk in this prefix
-      if (q_begin == 0) swept_local += c_binom[n - last - 1][K - P];  // 7-combinations sharing this prefix
       bool rejected = false;
 #pragma unroll
       for (int i = 0; i < P; i++) rejected |= (pre[i] < 8) && ((inmask >> pre[i]) & 1u);
-      if (rejected) continue;
+      if (rejected) {
+        // the reference steps through these one by one (lut.c:294-305): T-units all the same
+        if (q_begin == 0 && lane == 0) swept_lane += c_binom[n - last - 1][K - P];
+        continue;
+      }
 
       // mixed cells of the prefix (lane < NC = cell, first gate most significant)
       uint32_t mixed_ballot;
@@ -762,6 +869,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
         }
         const int ge = P == 4 ? last + 1 + pi : pre[P - 1];   // P == 5: e is the prefix's last gate
         const int gf = last + 1 + pj;
+        if (lane_ok) swept_lane += (unsigned long long)(n - 1 - gf);   // T-units: every g > f
         if (P == 4 && ge < 8 && ((inmask >> ge) & 1u)) lane_ok = false;
         if (gf < 8 && ((inmask >> gf) & 1u)) lane_ok = false;
         uint32_t te[NW], tf[NW];
@@ -773,8 +881,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
         // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
         // (SH: windows of 31 gates starting AT the smallest possible g, wb counts them)
         const int first_g = last + (K - P);
-        for (int wb = SH ? 0 : ((first_g >> 5) & ~(W - 1));
-             SH ? (first_g + 31 * wb < n) : (wb < ((n + 31) >> 5)); wb += W) {
+        const int wb0 = SH ? 0 : ((first_g >> 5) & ~(W - 1));
+        int nvw = 0;      // words of surviving-g vectors stored for this chunk
+        for (int wb = wb0; SH ? (first_g + 31 * wb < n) : (wb < ((n + 31) >> 5)); wb += W) {
           const int base = SH ? first_g + 31 * wb : 0;
           uint32_t V[W];
           if constexpr (SH) {
@@ -895,172 +1004,446 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 #pragma unroll
             for (int jw = 0; jw < W; jw++) alive |= V[jw] != 0;
           }
-          // emit every surviving g of every lane
-          int cnt = 0;
+          // park this window's survivors; the chunk is emitted once all its windows are done, so
+          // that a lane's hits come out in increasing g whatever the window they were found in
 #pragma unroll
-          for (int jw = 0; jw < W; jw++) cnt += __popc(V[jw]);
-          int incl = cnt;
+          for (int jw = 0; jw < W; jw++) vs[(nvw + jw) * 32 + lane] = V[jw];
+          nvw += W;
+        }
+        // emit the chunk: lane-major (= (e,f) order), then g ascending
+        int cnt = 0;
+        for (int i = 0; i < nvw; i++) cnt += __popc(vs[i * 32 + lane]);
+        int incl = cnt;
 #pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const int up = __shfl_up_sync(kFull, incl, d);
-            if (lane >= d) incl += up;
-          }
-          const int warp_total = __shfl_sync(kFull, incl, 31);
-          if (warp_total == 0) continue;
-          unsigned long long base_slot = 0;
-          if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)warp_total);
-          base_slot = __shfl_sync(kFull, base_slot, 0) + (unsigned long long)(incl - cnt);
-          uint64_t head = 0;
+        for (int d = 1; d < 32; d <<= 1) {
+          const int up = __shfl_up_sync(kFull, incl, d);
+          if (lane >= d) incl += up;
+        }
+        const int warp_total = __shfl_sync(kFull, incl, 31);
+        if (warp_total == 0) continue;
+        unsigned long long base_slot = 0;
+        if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)warp_total);
+        base_slot = __shfl_sync(kFull, base_slot, 0) + (unsigned long long)(incl - cnt);
+        uint64_t where = (b << 22) | (uint64_t)(tj + (uint32_t)(incl - cnt));   // (ticket, index in it)
+        uint64_t head = 0;
 #pragma unroll
-          for (int i = 0; i < P; i++) head = (head << 9) | (uint64_t)pre[i];
-          if (P == 4) {
-            head = (head << 27) | ((uint64_t)ge << 18) | ((uint64_t)gf << 9);
-          } else {
-            head = (head << 18) | ((uint64_t)gf << 9);
-          }
-#pragma unroll
-          for (int j = 0; j < W; j++) {
-            uint32_t v = V[j];
+        for (int i = 0; i < P; i++) head = (head << 9) | (uint64_t)pre[i];
+        if (P == 4) {
+          head = (head << 27) | ((uint64_t)ge << 18) | ((uint64_t)gf << 9);
+        } else {
+          head = (head << 18) | ((uint64_t)gf << 9);
+        }
+        if (cnt != 0) {
+          for (int i = 0; i < nvw; i++) {
+            uint32_t v = vs[i * 32 + lane];
+            const int g0 = SH ? first_g + 31 * i : (wb0 + i) * 32;
             while (v != 0) {
               const int gbit = __ffs(v) - 1;
               v &= v - 1;
               if (base_slot < hits_cap) {
-                hits[base_slot] = head | (uint64_t)(SH ? base + gbit : (wb + j) * 32 + gbit);
+                hits[base_slot] = head | (uint64_t)(g0 + gbit);
+                aux[base_slot] = where;
               } else {
                 atomicExch(&ctl->overflow, 1u);
               }
               base_slot++;
+              where++;
             }
           }
-          emitted += (unsigned long long)warp_total;
         }
+        tj += (uint32_t)warp_total;
+        emitted += (unsigned long long)warp_total;
         // One prefix never needs to contribute more than the list cap (lut.c:316-318); checked only
         // between chunks, when every pair up to here has all its g emitted.
         if (emitted >= list_cap) prefix_done = true;
       }
     }
+    }  // valid
+    if (lane == 0) {
+      tcount[b] = tj;
+      if (tj != 0) atomicAdd(&gcount[b >> 10], tj);
+    }
   }
-  if (lane == 0 && swept_local != 0) atomicAdd(&ctl->swept, swept_local);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) swept_lane += __shfl_xor_sync(kFull, swept_lane, d);
+  if (lane == 0 && swept_lane != 0) atomicAdd(&ctl->swept, swept_lane);
 }
 
 // ------------------------------------------------------------------------------------------------
-// Builds DevParams7::minpos3 from pos_middle (one CTA): entry (S,V) is the minimum, over the
-// completions of V on the bits outside S, of that function's position -- 4^8 lookups in all, no
-// synchronisation between entries.
-// Position-major rows of a staged problem (DevProblem::xr), from its gate-major tables: bit g of row
-// p = gate g at masked position p, the row complemented where the target is 0; with n <= 31 / n <= 63
-// the top bit of word 0 / 1 is no gate and carries the position's target bit ("free seen").
-__global__ void __launch_bounds__(256) k_build_rows(DevProblem *__restrict__ prob) {
-  const int n = prob->n;
-  const int m = prob->m;
-  const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= m * 16) return;
-  const int p = idx >> 4, gw = idx & 15;
-  const int w = p >> 5, j = p & 31;
-  uint32_t word = 0;
-  const int g_end = min(n, gw * 32 + 32);
-  for (int g = gw * 32; g < g_end; g++) word |= ((prob->tabs[w][g] >> j) & 1u) << (g & 31);
-  const bool t1 = ((prob->T[w] >> j) & 1u) != 0;
-  if (!t1) word = ~word;
-  if (spare >= 0 && gw == (spare >> 5)) word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
-  prob->xr[p][gw] = word;
+// Ordered list from ticket-tagged hits (see k_filter7_pm).  k_offsets: exclusive prefix sum of the
+// per-ticket hit counts, one CTA per group of 1,024 tickets (the group totals were accumulated by
+// the filter itself); k_scatter: every stored hit to its place, cut at the list cap
+// (lut.c:291,316-318).
+constexpr int kTicketGroup = 1024;
+
+__global__ void __launch_bounds__(256) k_offsets(DevCtl *__restrict__ ctl,
+    const uint32_t *__restrict__ tcount, const uint32_t *__restrict__ gcount,
+    uint32_t *__restrict__ toffset, unsigned long long tickets_cap, unsigned int list_cap,
+    unsigned int list_base) {
+  __shared__ unsigned long long s_part[8];
+  __shared__ uint32_t s_scan[8];
+  wait_for_predecessor();
+  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  const unsigned long long handed = min(volatile_load(&ctl->ticket), tickets_cap);
+  const unsigned long long first = (unsigned long long)blockIdx.x * kTicketGroup;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const unsigned long long total = (unsigned long long)list_base
+        + min(volatile_load(&ctl->hit_count), (unsigned long long)0xffffffffu);
+    ctl->list_count = (unsigned int)min(total, (unsigned long long)list_cap);
+  }
+  if (first >= handed) return;
+  // hits in front of this group
+  unsigned long long before = 0;
+  for (unsigned int g = threadIdx.x; g < blockIdx.x; g += blockDim.x) before += gcount[g];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) before += __shfl_xor_sync(kFull, before, d);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = before;
+  __syncthreads();
+  before = list_base;
+#pragma unroll
+  for (int i = 0; i < 8; i++) before += s_part[i];
+  // local scan: 4 consecutive tickets per thread
+  const unsigned long long t0 = first + 4ull * threadIdx.x;
+  uint32_t c[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) c[i] = t0 + i < handed ? tcount[t0 + i] : 0u;
+  const uint32_t mine = c[0] + c[1] + c[2] + c[3];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(kFull, incl, d);
+    if ((threadIdx.x & 31) >= d) incl += up;
+  }
+  if ((threadIdx.x & 31) == 31) s_scan[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t warp_base = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) warp_base += i < (int)(threadIdx.x >> 5) ? s_scan[i] : 0u;
+  unsigned long long off = before + warp_base + (incl - mine);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (t0 + i < handed) toffset[t0 + i] = (uint32_t)min(off, (unsigned long long)0xffffffffu);
+    off += c[i];
+  }
 }
 
+__global__ void __launch_bounds__(256) k_scatter(DevCtl *__restrict__ ctl,
+    const uint64_t *__restrict__ hits, const uint64_t *__restrict__ aux,
+    const uint32_t *__restrict__ toffset, uint64_t *__restrict__ sorted,
+    unsigned long long hits_cap, unsigned int list_cap) {
+  wait_for_predecessor();
+  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  if (volatile_load32(&ctl->overflow) == 1u) return;   // incomplete hit buffer: the host retries
+  const unsigned long long count = min(volatile_load(&ctl->hit_count), hits_cap);
+  for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < count;
+       s += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint64_t where = aux[s];
+    const unsigned long long pos = (unsigned long long)toffset[where >> 22] + (where & 0x3fffffu);
+    if (pos < list_cap) sorted[pos] = hits[s];
+  }
+}
+
+// Merge of `nruns` ascending runs of packed tuples (the per-part lists of a sharded phase 1, laid
+// out run r at src + r * stride, counts[r] entries) into one ascending list cut at list_cap: an
+// entry's place is its index in its own run plus the number of smaller entries in every other run
+// (binary searches; entries are distinct).  The device-side counterpart of lut.c:329-349.
+constexpr int kMaxRuns = 64;
+struct RunCounts { uint32_t n[kMaxRuns]; };
+
+__global__ void __launch_bounds__(256) k_merge_runs(const uint64_t *__restrict__ src,
+    unsigned long long stride, RunCounts counts, int nruns, uint64_t *__restrict__ dst,
+    unsigned int list_cap, DevCtl *__restrict__ ctl) {
+  unsigned long long total = 0;
+  for (int r = 0; r < nruns; r++) total += counts.n[r];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->list_count = (unsigned int)min(total, (unsigned long long)list_cap);
+  }
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    int r = 0;
+    unsigned long long idx = i;
+    while (idx >= counts.n[r]) {
+      idx -= counts.n[r];
+      r++;
+    }
+    const uint64_t v = src[(unsigned long long)r * stride + idx];
+    unsigned long long pos = idx;
+    for (int o = 0; o < nruns; o++) {
+      if (o == r) continue;
+      const uint64_t *run = src + (unsigned long long)o * stride;
+      uint32_t lo = 0, hi = counts.n[o];
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (run[mid] < v) lo = mid + 1; else hi = mid;
+      }
+      pos += lo;
+    }
+    if (pos < list_cap) dst[pos] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// First kernel of every call chain.
+//
 // Per-call inputs travel as kernel arguments, not as separate host->device copies: a copy-engine
 // transfer of a few hundred bytes costs several microseconds of stream latency, and a real run is
 // thousands of searches that last tens of microseconds each.
-struct Pos256 { uint8_t b[256]; };
-struct Pos512 { uint8_t outer[256]; uint8_t middle[256]; };
+constexpr int kArgGates = 40;   // gate tables that fit the kernel arguments next to everything else
+struct BeginArgs {
+  uint8_t pos5[256];       // search_5lut: position of each function in the shuffled order
+  uint8_t pos_outer[256];  // search_7lut
+  uint8_t pos_middle[256];
+  uint16_t order3[512];    // 3-LUT scan: the caller's shuffled gate order (lut.c:501-507)
+  unsigned long long seq;
+  uint32_t flags;          // kBegin* bits
+  uint32_t gcount_n;       // ticket-group counters to clear
+  // problem delta (kBeginProblem): the state is n gates under (target, mask, inmask); gates
+  // a_first .. a_first + a_count - 1 travel in newg (the others are resident, or were copied into
+  // DevProblem::full before the launch); gates from c_first on are (re)compressed.
+  int32_t n;
+  uint32_t inmask;
+  int32_t a_first, a_count;
+  int32_t c_first;
+  uint32_t target[8];
+  uint32_t mask[8];
+  uint32_t newg[kArgGates][8];
+};
+constexpr uint32_t kBeginScan3 = 1, kBeginSearch5 = 2, kBeginSearch7 = 4, kBeginRows = 8,
+    kBeginKeepCtl = 16, kBeginOrder3 = 32, kBeginProblem = 64;
 
-__device__ __forceinline__ void reset_ctl_words(DevCtl *ctl) {
-  DevCtl c;
-  memset(&c, 0, sizeof(c));
-  c.best = ~0ull;
-  c.stop_ticket = ~0ull;
-  *ctl = c;
-}
-
-// First kernel of a search_5lut call: installs the position table, resets the control words.
-__global__ void __launch_bounds__(256) k_begin5(DevCtl *__restrict__ ctl, uint8_t *__restrict__ pos5,
-    const Pos256 pos) {
-  pos5[threadIdx.x] = pos.b[threadIdx.x];
-  if (threadIdx.x == 0) reset_ctl_words(ctl);
-}
-
-// First kernel of a search_7lut call / of its phase 2.  `pos` = the two inverse permutations;
-// reset != 0 also resets the control words.
-__global__ void __launch_bounds__(1024) k_prepare7(DevParams7 *__restrict__ par,
-    DevCtl *__restrict__ ctl, const Pos512 pos, int reset) {
-  __shared__ uint8_t posm[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    posm[i] = pos.middle[i];
-    par->pos_middle[i] = pos.middle[i];
-    par->pos_outer[i] = pos.outer[i];
+// Derives the search's working set from the resident uncompressed tables (CTAs 1.. of k_begin, or
+// all CTAs of k_prepare_problem): tables compressed to the masked positions (word-major tabs, T, M;
+// every test of the path is "under the mask", lut.c:38-42,86), the header, and -- when asked -- the
+// position-major rows xr: bit g of row p = gate g at masked position p, the row complemented where
+// the target is 0; with n <= 31 / n <= 63 the top bit of word 0 / 1 is no gate and carries the
+// position's target bit.  No CTA depends on another's output: a thread reads a gate from the
+// arguments if it travels there, else from DevProblem::full (which this launch writes for the
+// travelling gates only).
+__device__ __forceinline__ void prepare_problem(DevProblem *__restrict__ prob, const BeginArgs &a,
+    int cta, int nctas) {
+  __shared__ uint8_t s_posn[256];   // i-th masked position
+  __shared__ uint32_t s_mask[8], s_target[8];
+  if (threadIdx.x < 8) {
+    s_mask[threadIdx.x] = a.mask[threadIdx.x];
+    s_target[threadIdx.x] = a.target[threadIdx.x];
   }
-  if (threadIdx.x == 0 && reset != 0) reset_ctl_words(ctl);
   __syncthreads();
-  for (int e = threadIdx.x; e < kMinpos3; e += blockDim.x) {
-    uint32_t free_bits = 0, forced = 0;
-    int rest = e;
+  int m = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int d = rest % 3;
-      rest /= 3;
-      if (d == 0) free_bits |= 1u << j;
-      if (d == 2) forced |= 1u << j;
+  for (int w = 0; w < 8; w++) m += __popc(s_mask[w]);
+  if (threadIdx.x < 256) {
+    const int p = threadIdx.x, w = p >> 5, j = p & 31;
+    if ((s_mask[w] >> j) & 1u) {
+      int idx = __popc(s_mask[w] & ((1u << j) - 1u));
+      for (int k = 0; k < w; k++) idx += __popc(s_mask[k]);
+      s_posn[idx] = (uint8_t)p;
     }
-    uint32_t best = posm[forced];
-    for (uint32_t sub = free_bits; sub != 0; sub = (sub - 1) & free_bits) {
-      best = min(best, (uint32_t)posm[forced | sub]);
-    }
-    par->minpos3[e] = (uint8_t)best;
   }
+  __syncthreads();
+  const int n = a.n;
+  const int nw = m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 4 : 8;
+  auto gate_word = [&](int g, int w) -> uint32_t {
+    const int k = g - a.a_first;
+    return (k >= 0 && k < a.a_count) ? a.newg[k][w] : prob->full[g][w];
+  };
+  if (cta == 0 && threadIdx.x < 8) {
+    const int w = threadIdx.x;
+    uint32_t t = 0, mm = 0;
+    for (int i = 0; i < 32; i++) {
+      const int ci = w * 32 + i;
+      if (ci < m) {
+        const int p = s_posn[ci];
+        t |= ((s_target[p >> 5] >> (p & 31)) & 1u) << i;
+        mm |= 1u << i;
+      }
+    }
+    prob->T[w] = t;
+    prob->M[w] = mm;
+    prob->target_full[w] = s_target[w];
+    prob->mask_full[w] = s_mask[w];
+    if (w == 0) {
+      prob->n = n;
+      prob->nw = nw;
+      prob->inmask = a.inmask;
+      prob->m = m;
+    }
+  }
+  const int tid = cta * blockDim.x + threadIdx.x;
+  const int nthreads = nctas * blockDim.x;
+  // compressed tables: one thread per (gate, word); all 8 words are written (zero above nw) so that
+  // no stale bits survive a change of mask
+  for (int it = tid; it < (n - a.c_first) * 8; it += nthreads) {
+    const int g = a.c_first + (it >> 3), w = it & 7;
+    uint32_t out = 0;
+    if (w < nw) {
+      uint32_t src[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) src[k] = gate_word(g, k);
+      for (int i = 0; i < 32; i++) {
+        const int ci = w * 32 + i;
+        if (ci >= m) break;
+        const int p = s_posn[ci];
+        uint32_t word = src[0];
+#pragma unroll
+        for (int k = 1; k < 8; k++) word = (p >> 5) == k ? src[k] : word;
+        out |= ((word >> (p & 31)) & 1u) << i;
+      }
+    }
+    prob->tabs[w][g] = out;
+    // the travelling gates become resident
+    if (g >= a.a_first && g < a.a_first + a.a_count) prob->full[g][w] = a.newg[g - a.a_first][w];
+  }
+  if (a.flags & kBeginRows) {
+    const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
+    for (int it = tid; it < m * 16; it += nthreads) {
+      const int p = it >> 4, gw = it & 15;
+      const int pp = s_posn[p];
+      uint32_t word = 0;
+      const int g_end = min(n, gw * 32 + 32);
+      for (int g = gw * 32; g < g_end; g++) {
+        word |= ((gate_word(g, pp >> 5) >> (pp & 31)) & 1u) << (g & 31);
+      }
+      const bool t1 = ((s_target[pp >> 5] >> (pp & 31)) & 1u) != 0;
+      if (!t1) word = ~word;
+      if (spare >= 0 && gw == (spare >> 5)) word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
+      prob->xr[p][gw] = word;
+    }
+  }
+}
+
+// sbg_stage_problem: makes a state resident AND ready (derived data built) ahead of the searches.
+__global__ void __launch_bounds__(1024) k_prepare_problem(DevProblem *__restrict__ prob,
+    const BeginArgs a) {
+  prepare_problem(prob, a, blockIdx.x, gridDim.x);
+}
+
+// CTA 0: control words, position tables, ticket-group counters, and minpos3 (see DevParams7) by
+// dynamic programming over the number of unconstrained bits: an entry with a free bit j is the
+// minimum of the two entries that force bit j (entries are visited level by level through
+// DevTables::m3_info, which lists them by number of free bits).
+// CTAs 1..: the problem block (prepare_problem) when the state changed or its rows are needed.
+__global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, DevParams7 *__restrict__ par, uint8_t *__restrict__ pos5,
+    uint16_t *__restrict__ order3, uint32_t *__restrict__ gcount,
+    const DevTables *__restrict__ tab, const BeginArgs a) {
+  if (blockIdx.x != 0) {
+    prepare_problem(prob, a, blockIdx.x - 1, gridDim.x - 1);
+    return;
+  }
+  __shared__ uint8_t posm[256];
+  __shared__ uint8_t s_min[kMinpos3 + 3];
+  if (threadIdx.x == 0) {
+    if (a.flags & kBeginKeepCtl) {   // phase 2 on an installed list: keep the list, restart the rest
+      ctl->best = ~0ull;
+      ctl->ticket2 = 0;
+      ctl->ctas_done = 0;
+      ctl->stage_found = 0;
+      ctl->overflow = 0;
+      ctl->skip7 = 0;
+      ctl->seq = a.seq;
+    } else {
+      DevCtl c;
+      memset(&c, 0, sizeof(c));
+      c.best = ~0ull;
+      c.stop_ticket = ~0ull;
+      c.seq = a.seq;
+      c.skip5 = (a.flags & kBeginSearch5) ? 0u : 1u;
+      c.skip7 = (a.flags & kBeginSearch7) ? 0u : 1u;
+      *ctl = c;
+    }
+  }
+  if (!(a.flags & kBeginKeepCtl)) {
+    for (uint32_t i = threadIdx.x; i < a.gcount_n; i += blockDim.x) gcount[i] = 0;
+  }
+  if (a.flags & kBeginSearch5) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) pos5[i] = a.pos5[i];
+  }
+  if (a.flags & kBeginOrder3) {
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) order3[i] = a.order3[i];
+  }
+  if (!(a.flags & kBeginSearch7)) return;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    posm[i] = a.pos_middle[i];
+    par->pos_middle[i] = a.pos_middle[i];
+    par->pos_outer[i] = a.pos_outer[i];
+  }
+  __syncthreads();
+  int lo = 0;
+  for (int level = 0; level <= 8; level++) {
+    const int hi = tab->m3_level[level + 1];
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+      const uint32_t info = tab->m3_info[i];
+      const uint32_t e = info & 0x1fffu;
+      if (level == 0) {
+        s_min[e] = posm[info >> 16];
+      } else {
+        const uint32_t step = info >> 16;   // 3^j of the lowest free bit j
+        s_min[e] = min(s_min[e + step], s_min[e + 2 * step]);
+      }
+    }
+    lo = hi;
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < kMinpos3; e += blockDim.x) par->minpos3[e] = s_min[e];
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ordering the phase-1 hits (lut.c:329-349 concatenates per-rank lists in rank order, which at
-// size 1 is lexicographic order).  Short lists -- the common case -- are sorted by one CTA with a
-// bitonic network in shared memory, the count being read on the device so that phase 2 can be
-// launched without a host round trip; longer lists go through CUB on the host's initiative.
-constexpr int kSmallSort = 4096;
-
-__global__ void __launch_bounds__(1024) k_sort_small(const uint64_t *__restrict__ hits,
-    uint64_t *__restrict__ sorted, DevCtl *__restrict__ ctl, unsigned int list_cap) {
-  __shared__ uint64_t keys[kSmallSort];
-  const unsigned long long total = ctl->hit_count;
-  if (total > (unsigned long long)kSmallSort || ctl->overflow != 0) {
-    if (threadIdx.x == 0) {
-      ctl->sorted_ok = 0;
-      ctl->list_count = 0;
-    }
-    return;
-  }
-  const unsigned int cnt = (unsigned int)total;
-  unsigned int npow = 1;
-  while (npow < cnt) npow <<= 1;
-  for (unsigned int i = threadIdx.x; i < npow; i += blockDim.x) keys[i] = i < cnt ? hits[i] : ~0ull;
+// The 3-LUT scan of lut_search (lut.c:501-523): the first triple (i < k < m, as positions in the
+// caller's shuffled gate order) whose three gates admit SOME 3-input function equal to the target
+// under the mask (check_n_lut_possible(3, ...); get_lut_function then always succeeds).  One thread
+// per triple, tickets in order, minimum rank of the position triple in ctl->best; closes stage 0.
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_scan3(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const uint16_t *__restrict__ order3) {
+  extern __shared__ uint32_t smem[];
+  wait_for_predecessor();
+  const int n = prob->n;
+  const int npad = (n + 3) & ~3;
+  uint32_t *s_tabs = smem;
+  uint16_t *s_order = reinterpret_cast<uint16_t *>(smem + NW * npad);
+  stage_tables(s_tabs, prob, NW, npad);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_order[i] = order3[i];
   __syncthreads();
-  for (unsigned int k = 2; k <= npow; k <<= 1) {
-    for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-      for (unsigned int i = threadIdx.x; i < npow; i += blockDim.x) {
-        const unsigned int ixj = i ^ j;
-        if (ixj > i) {
-          const uint64_t a = keys[i], b = keys[ixj];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) {
-            keys[i] = b;
-            keys[ixj] = a;
-          }
-        }
+  uint32_t T[NW], M[NW];
+#pragma unroll
+  for (int w = 0; w < NW; w++) {
+    T[w] = prob->T[w];
+    M[w] = prob->M[w];
+  }
+  const uint64_t total = c_binom[n][3];
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    if (volatile_load(&ctl->best) < t) break;   // a smaller triple already matched
+    int pos[3];
+    uint64_t unused;
+    unrank_prefix<3, 3>(t, n, pos, unused);
+    const int ga = s_order[pos[0]], gb = s_order[pos[1]], gc = s_order[pos[2]];
+    uint32_t ones[8], zeros[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) ones[c] = zeros[c] = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+      const uint32_t ta = s_tabs[w * npad + ga], tb = s_tabs[w * npad + gb],
+          tc = s_tabs[w * npad + gc];
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint32_t cell = M[w] & ((c & 4) ? ta : ~ta) & ((c & 2) ? tb : ~tb)
+            & ((c & 1) ? tc : ~tc);
+        ones[c] |= cell & T[w];
+        zeros[c] |= cell & ~T[w];
       }
-      __syncthreads();
+    }
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < 8; c++) ok &= !(ones[c] != 0 && zeros[c] != 0);
+    if (ok) {
+      atomicMin(&ctl->best, (unsigned long long)t);
+      break;   // this thread's later triples are larger
     }
   }
-  for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x) sorted[i] = keys[i];
-  if (threadIdx.x == 0) {
-    ctl->list_count = cnt < list_cap ? cnt : list_cap;
-    ctl->sorted_ok = 1;
+  let_successor_start();
+  if (last_cta_of_grid(ctl) && threadIdx.x == 0) {
+    close_stage(ctl, out, 0, volatile_load(&ctl->best), 0, 0, 0);
   }
 }
 
@@ -1124,8 +1507,8 @@ __device__ __forceinline__ void tuple_summary(const uint32_t *s_tabs, int npad, 
 
 template <int NW>
 __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, const DevParams7 *__restrict__ par, const uint64_t *__restrict__ list,
-    unsigned int count, int part, int nparts, const DevTables *__restrict__ tab) {
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const DevParams7 *__restrict__ par,
+    const uint64_t *__restrict__ list, int part, int nparts, const DevTables *__restrict__ tab) {
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_minpos[kMinpos3 + 3];
   __shared__ uint16_t s_p3[256];
@@ -1134,25 +1517,11 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   __shared__ uint32_t s_src7[25 * 32];   // copy of DevTables::src7
   __shared__ uint32_t s_H[kWarpsPerCta][24];
 
-  if (count == 0xffffffffu) {  // list produced on the device by k_sort_small
-    if (ctl->sorted_ok == 0) return;
-    count = ctl->list_count;
-  }
-  // this part's share is ceil((count - part) / nparts) entries; surplus CTAs leave at once
-  const unsigned int share = count > (unsigned int)part
-      ? (count - (unsigned int)part + (unsigned int)nparts - 1) / (unsigned int)nparts : 0u;
-  if (blockIdx.x * kWarpsPerCta >= share) return;
-
-  const int n = prob->n;
-  const int npad = (n + 3) & ~3;
-  uint32_t *s_tabs = smem;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-
-  for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_minpos[i] = par->minpos3[i];
+  // independent of the chain's earlier kernels: overlaps their tail under programmatic launch
   for (int i = threadIdx.x; i < 25 * 32; i += blockDim.x) s_src7[i] = tab->src7[i >> 5][i & 31];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-    s_pos[i] = par->pos_outer[i];
     int p3 = 0, w3 = 1;
     for (int j = 0; j < 8; j++) {
       if ((i >> j) & 1) p3 += w3;
@@ -1160,7 +1529,23 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
     }
     s_p3[i] = (uint16_t)p3;
   }
+  wait_for_predecessor();
+  const int n = prob->n;
+  const int npad = (n + 3) & ~3;
+  uint32_t *s_tabs = smem;
   stage_tables(s_tabs, prob, NW, npad);
+
+  // the list length is on the device (k_offsets / k_merge_runs); this part's share is
+  // ceil((count - part) / nparts) entries, surplus CTAs have nothing to do
+  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0
+      || volatile_load32(&ctl->overflow) != 0;
+  const unsigned int count = skip ? 0u : ctl->list_count;
+  const unsigned int share = count > (unsigned int)part
+      ? (count - (unsigned int)part + (unsigned int)nparts - 1) / (unsigned int)nparts : 0u;
+  if (blockIdx.x * kWarpsPerCta < share) {
+  for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_minpos[i] = par->minpos3[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = par->pos_outer[i];
+  __syncthreads();
 
   uint32_t T[NW], M[NW];
 #pragma unroll
@@ -1335,6 +1720,19 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
       if (lane == 0) atomicMin(&ctl->best, (unsigned long long)key);
       break;  // later tickets of this warp have larger list indices
     }
+  }
+  }  // this CTA has a share
+  let_successor_start();
+  if (last_cta_of_grid(ctl) && threadIdx.x == 0
+      && volatile_load32(&ctl->stage_found) == 0 && volatile_load32(&ctl->skip7) == 0) {
+    const unsigned long long key = volatile_load(&ctl->best);
+    unsigned long long tuple = 0, tuple_prev = 0;
+    if (key != ~0ull) {
+      const unsigned long long idx = key >> 23;
+      tuple = list[idx];
+      if (idx > 0) tuple_prev = list[idx - 1];
+    }
+    close_stage(ctl, out, 2, key, ctl->list_count, tuple, tuple_prev);
   }
 }
 

@@ -13,7 +13,8 @@ from typing import List
 import numpy as np
 
 from . import native
-from .native import SbgResult, NativeLibraryError, SBG_KEY_NONE, SBG_LIST_CAP
+from .native import (SbgResult, SbgJob, SbgNodeResult, NativeLibraryError, SBG_KEY_NONE,
+                     SBG_LIST_CAP, SBG_DO_SCAN3, SBG_DO_SEARCH5, SBG_DO_SEARCH7)
 
 NO_GATE = 0xFFFF  # state.h:30
 
@@ -136,6 +137,22 @@ class LutEngine:
     def kernel_ms(self, which):
         return float(self.lib.sbg_last_kernel_ms(self._h, which))
 
+    def set_timing(self, on):
+        """Kernel-family timing (CUDA events inside the chains; off by default)."""
+        self._check(self.lib.sbg_set_timing(self._h, 1 if on else 0))
+
+    def transfer_stats(self):
+        """(h2d bytes, d2h bytes, bulk uploads, incremental uploads, unchanged states) so far."""
+        out = (C.c_uint64 * 5)()
+        self._check(self.lib.sbg_transfer_stats(self._h, out))
+        return [int(x) for x in out]
+
+    def alu_peak(self):
+        """Measured LOP3 issue rate of the device, warp instructions per second."""
+        v = C.c_double()
+        self._check(self.lib.sbg_alu_peak(self._h, C.byref(v)))
+        return float(v.value)
+
     # -- problem -------------------------------------------------------------------------------
     def load(self, tables, target, mask, inbits):
         tables, tp = _u64(tables)
@@ -176,6 +193,67 @@ class LutEngine:
         self._check(self.lib.sbg_search7(self._h, _order_ptr(outer_order),
                                          _order_ptr(middle_order), C.byref(res)))
         return res
+
+    # -- one call per node / batches of nodes --------------------------------------------------
+    @staticmethod
+    def _job(slot, order5=None, outer=None, middle=None, gate_order=None):
+        """Builds an SbgJob; returns (job, keepalive buffers)."""
+        job = SbgJob()
+        keep = []
+        job.slot = slot
+        flags = 0
+        if gate_order is not None:
+            go = (C.c_uint16 * len(gate_order))(*[int(g) for g in gate_order])
+            keep.append(go)
+            job.gate_order = C.cast(go, C.POINTER(C.c_uint16))
+            flags |= SBG_DO_SCAN3
+        if order5 is not None:
+            b = _order_ptr(order5)
+            keep.append(b)
+            job.order5 = C.cast(b, C.POINTER(C.c_uint8))
+            flags |= SBG_DO_SEARCH5
+        if outer is not None:
+            bo, bm = _order_ptr(outer), _order_ptr(middle)
+            keep += [bo, bm]
+            job.outer7 = C.cast(bo, C.POINTER(C.c_uint8))
+            job.middle7 = C.cast(bm, C.POINTER(C.c_uint8))
+            flags |= SBG_DO_SEARCH7
+        job.flags = flags
+        return job, keep
+
+    def search_node(self, slot=0, order5=None, outer=None, middle=None, gate_order=None):
+        """scan3 -> search_5lut -> search_7lut of one staged state as one device call chain."""
+        job, keep = self._job(slot, order5, outer, middle, gate_order)
+        res = SbgNodeResult()
+        self._check(self.lib.sbg_search_node(self._h, C.byref(job), C.byref(res)))
+        return res
+
+    def search_batch(self, jobs):
+        """jobs: list of dicts with keys slot, order5, outer, middle, gate_order (any may be absent).
+        Returns the list of SbgNodeResult, one per job."""
+        arr = (SbgJob * len(jobs))()
+        keep = []
+        for i, j in enumerate(jobs):
+            job, k = self._job(j.get("slot", 0), j.get("order5"), j.get("outer"), j.get("middle"),
+                               j.get("gate_order"))
+            arr[i] = job
+            keep.append(k)
+        res = (SbgNodeResult * len(jobs))()
+        self._check(self.lib.sbg_search_batch(self._h, len(jobs), arr, res))
+        return list(res)
+
+    def list7_device(self):
+        """(device pointer, count) of this device's ordered phase-1 list."""
+        ptr = C.c_void_p()
+        cnt = C.c_int()
+        self._check(self.lib.sbg_list7_device(self._h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def set_list7_device(self, dev_ptr, stride, counts):
+        """Merges ascending runs already in device memory (run r at dev_ptr + 8 * r * stride)."""
+        arr = (C.c_int * len(counts))(*[int(c) for c in counts])
+        self._check(self.lib.sbg_set_list7_device(self._h, C.c_void_p(dev_ptr), int(stride), arr,
+                                                  len(counts)))
 
     # -- sharded building blocks ---------------------------------------------------------------
     def search5_part(self, part, nparts, func_order):
@@ -283,3 +361,55 @@ def search_7lut(engine, tables, target, mask, inbits, rng):
     outer, middle = shuffled_orders7(rng)
     engine.load(tables, target, mask, inbits)
     return result7_to_ret(engine.search7(outer, middle), rng)
+
+
+@dataclass
+class LutSearchResult:
+    """What lut_search() would add to the graph (lut.c:489-631): `luts` = the add_lut calls in
+    order, each (function, in1, in2, in3) with inputs either gate numbers or ("new", k) = the k-th
+    LUT added by this call; `stage` = 3, 5, 7 or 0 (NO_GATE)."""
+    stage: int
+    luts: List[tuple] = field(default_factory=list)
+    node: object = None
+
+
+def lut_search(engine, tables, target, mask, inbits, gate_order, rng, allow5=True, allow7=True):
+    """lut.c:489-631 as ONE device call: the 3-LUT scan over the caller's shuffled gate order
+    (lut.c:501-523), search_5lut (lut.c:553) and search_7lut (lut.c:593), each only if the earlier
+    ones found nothing.  allow5 / allow7 = check_num_gates_possible(st, 2 / 3) (lut.c:525, 582).
+
+    RNG: the reference draws 256 values on entry to search_5lut and 512 before phase 2 of
+    search_7lut, plus one per solved LUT with unseen cells (lut.c:104-106).  Which of those happen
+    depends on the stages' outcomes, so the shuffles are computed from a COPY of the generator
+    (looking ahead) and the real one is advanced afterwards by exactly what the reference would
+    have consumed."""
+    n = len(tables)
+    ahead = rng.copy()
+    order5 = shuffled_order(ahead) if (allow5 and n >= 5) else None
+    outer = middle = None
+    if allow5 and allow7 and n >= 7:
+        outer, middle = shuffled_orders7(ahead)
+    engine.load(tables, target, mask, inbits)
+    node = engine.search_node(0, order5, outer, middle, gate_order)
+    if node.found_stage == 3:
+        fi = node.func3
+        if node.seen3 != 0xFF:
+            fi |= (~node.seen3 & 0xFF) & (rng.next() & 0xFF)
+        return LutSearchResult(3, [(fi, int(node.gates3[0]), int(node.gates3[1]),
+                                    int(node.gates3[2]))], node)
+    if order5 is None:
+        return LutSearchResult(0, [], node)
+    for _ in range(256):
+        rng.next()
+    if node.found_stage == 5:
+        r = result5_to_ret(node.r5, rng).ret
+        return LutSearchResult(5, [(r[0], r[2], r[3], r[4]), (r[1], ("new", 0), r[5], r[6])], node)
+    if outer is None:
+        return LutSearchResult(0, [], node)
+    for _ in range(512):
+        rng.next()
+    if node.found_stage == 7:
+        r = result7_to_ret(node.r7, rng).ret
+        return LutSearchResult(7, [(r[0], r[3], r[4], r[5]), (r[1], r[6], r[7], r[8]),
+                                   (r[2], ("new", 0), ("new", 1), r[9])], node)
+    return LutSearchResult(0, [], node)

@@ -28,6 +28,20 @@ class SbgResult(C.Structure):
     ]
 
 
+class SbgJob(C.Structure):
+    _fields_ = [("slot", C.c_int32), ("flags", C.c_int32), ("order5", C.POINTER(C.c_uint8)),
+                ("outer7", C.POINTER(C.c_uint8)), ("middle7", C.POINTER(C.c_uint8)),
+                ("gate_order", C.POINTER(C.c_uint16))]
+
+
+class SbgNodeResult(C.Structure):
+    _fields_ = [("found_stage", C.c_int32), ("gates3", C.c_uint16 * 3), ("func3", C.c_uint8),
+                ("seen3", C.c_uint8), ("key3", C.c_uint64), ("r5", SbgResult), ("r7", SbgResult)]
+
+
+SBG_DO_SCAN3, SBG_DO_SEARCH5, SBG_DO_SEARCH7 = 1, 2, 4
+SBG_LANES = 8
+
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
 i8p = C.POINTER(C.c_int8)
@@ -42,6 +56,15 @@ SIGNATURES = {
     "sbg_plan_tickets": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint64,
                                    C.POINTER(C.c_uint64)]),
     "sbg_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_int]),
+    "sbg_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
+    "sbg_transfer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "sbg_alu_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "sbg_search_node": (C.c_int, [C.c_void_p, C.POINTER(SbgJob), C.POINTER(SbgNodeResult)]),
+    "sbg_search_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SbgJob),
+                                   C.POINTER(SbgNodeResult)]),
+    "sbg_list7_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "sbg_set_list7_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int),
+                                       C.c_int]),
     "sbg_load_problem": (C.c_int, [C.c_void_p, u64p, C.c_int, u64p, u64p, i8p]),
     "sbg_stage_problem": (C.c_int, [C.c_void_p, C.c_int, u64p, C.c_int, u64p, u64p, i8p]),
     "sbg_use_problem": (C.c_int, [C.c_void_p, C.c_int]),

@@ -42,3 +42,10 @@ class Xorshift1024:
         return (self.s[self.p] * self.MULT) & MASK64
 
     __call__ = next
+
+    def copy(self):
+        """An independent generator in the same state (used to look ahead without consuming)."""
+        r = Xorshift1024(list(self.s))
+        r.p = self.p
+        r.draws = self.draws
+        return r

@@ -365,3 +365,23 @@ def mux_mask(fixed):
         if all(((p >> b) & 1) == v for b, v in fixed):
             words[p >> 6] |= np.uint64(1) << np.uint64(p & 63)
     return words
+
+
+def oracle_check(num, target, mask, tables):
+    """check_n_lut_possible (lut.c:34-66) of the CPU oracle; tables: list of `num` 4-word arrays."""
+    lib = oracle_lib()
+    target, gp = _u64(target)
+    mask, mp = _u64(mask)
+    tabs, tp = _u64(np.stack(tables))
+    return bool(lib.orc_check_n_lut_possible(num, gp, mp, tp))
+
+
+def oracle_get_lut_function(in1, in2, in3, target, mask, rng, randomize=True):
+    """get_lut_function (lut.c:79-109) of the CPU oracle: (ok, func); rng advanced as the reference
+    would (one draw iff the solved function has unconstrained bits)."""
+    lib = oracle_lib()
+    arrs = [_u64(x) for x in (in1, in2, in3, target, mask)]
+    func = C.c_uint8()
+    ok = lib.orc_get_lut_function(*[a[1] for a in arrs], 1 if randomize else 0, C.byref(rng),
+                                  C.byref(func))
+    return bool(ok), int(func.value)

@@ -184,9 +184,10 @@ def test_paths_agree(engine):
         assert whole.tuples_feasible == count
 
 
-def test_sweep_and_position_major_kernels_agree(engine):
-    """Phase 1 has two implementations (bitmap sweep k_sweep<NW,5>, position-major k_filter7_pm);
-    their hit lists must be identical."""
+def test_launch_modes_agree(engine):
+    """The kernels of a chain are launched with programmatic dependent launch (each starts while its
+    predecessor drains); with SBG_PDL=0 they are plainly stream-ordered, with SBG_TIMING=1 events sit
+    between them.  Hit lists and search results must be identical in all three modes."""
     import subprocess
     import sys
     code = (
@@ -194,18 +195,21 @@ def test_sweep_and_position_major_kernels_agree(engine):
         "import _support as S, sboxgates_b200 as sb\n"
         "eng = sb.LutEngine(0); sbox = S.rijndael_sbox(); out = []\n"
         "for n, fixed in [(18, []), (24, [(0,1)]), (30, [(1,0),(4,1)]), (40, [(2,1),(3,0),(6,1)]), (44, [(5, 1)])]:\n"
-        "    eng.load(S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed])\n"
+        "    tabs, tgt, mask, inb = S.synthetic_state(n, seed=n), S.sbox_target(sbox, n %% 8), S.mux_mask(fixed), [b for b, _ in fixed]\n"
+        "    eng.load(tabs, tgt, mask, inb)\n"
         "    out.append(eng.filter7_part(0, 1).tolist())\n"
+        "    seed = np.random.RandomState(n).bytes(128)\n"
+        "    for fn in (sb.search_5lut, sb.search_7lut):\n"
+        "        r = fn(eng, tabs, tgt, mask, inb, sb.Xorshift1024(seed)); out.append([int(r.found)] + [int(x) for x in r.ret])\n"
         "import json; print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
-    lists = {}
-    for mode in ("pm", "sweep"):
-        env = dict(os.environ, SBG_FILTER=mode)
-        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
-                             check=True)
-        lists[mode] = res.stdout.strip().splitlines()[-1]
-    assert lists["pm"] == lists["sweep"]
+    outs = {}
+    for mode, env in (("pdl", {}), ("plain", {"SBG_PDL": "0"}), ("timed", {"SBG_TIMING": "1"})):
+        res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env),
+                             capture_output=True, text=True, check=True)
+        outs[mode] = res.stdout.strip().splitlines()[-1]
+    assert outs["pdl"] == outs["plain"] == outs["timed"]
     import json
-    assert sum(len(x) for x in json.loads(lists["pm"])) > 0
+    assert sum(len(x) for x in json.loads(outs["pdl"])[0::3]) > 0
 
 
 def test_hit_buffer_overflow_is_retried(monkeypatch):
