@@ -18,11 +18,14 @@ a per-tuple summary.  value = (T + C) / s; both are also reported separately.
 
 N > 1 (torchrun, one rank per GPU): the search states of a step are independent (in the program
 they are the 16 mux branches of create_circuit, the 8 output bits of -o -1 and the -i iterations),
-so every rank takes `--batch` states of a step of N x `--batch` and the ranks exchange only the
-result keys (one all-gather per step) -- weak scaling.  `--shard tuples` instead keeps `--batch`
-states in total and shards every single search over the ranks' GPUs (work items dealt round-robin;
-one all-gather of the 7-LUT hit lists and one all-reduce(MIN) per search phase) -- strong scaling
-of one search, which only pays for searches far larger than n = 40.
+so every rank takes `--batch` states of a step of N x `--batch` -- its own sbg_search_batch call --
+and the ranks exchange only the result keys (one non-blocking all-gather per step): weak scaling.
+The same line carries a `sharded` record: ONE search of a large state (n = 96, 128) sharded over the
+ranks' GPUs across the tuple space (work items dealt round-robin; the 7-LUT hit lists all-gathered
+and merged on the devices, one all-reduce(MIN) per search phase), with the one-GPU time of the same
+search beside it and the results compared in the run -- strong scaling of north_star's partition.
+Further records on one GPU: `replay` (recorded real calls of seeded reference runs through the C
+ABI, results asserted), `graph` (wall-clock to graph: the drop-in CLI on BASELINE.json configs[1]).
 
 --impl reference times the reference's own object code (oracle/_ref/libsbgref.so, built from the
 unmodified sources; the oracle port if that is absent) on the host cores, one process per core, each
@@ -194,35 +197,43 @@ class ClockSampler:
 # CPU arm: the reference's own object code on the host cores
 
 def _cpu_worker(args):
-    """One host core: the reference's search_5lut + search_7lut on the first n' gates of one
-    state.  Returns (seconds, T-units, C-units)."""
-    kind, tables, target, mask, inbits, seed = args
+    """One host core: the reference's search_5lut + search_7lut on samples (the first n' gates of a
+    workload state), one after the other until the deadline.  Returns (seconds, T-units, C-units,
+    samples done); the units of a sample are counted only when it completed."""
+    kind, samples, deadline_s = args
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _support as S
-    rng = S.OrcRng.from_seed(seed)
-    t_units = c_units = 0
-    t0 = time.perf_counter()
     if kind == "reference":
         S.ref_lib()
-        f5, r5, _ = S.ref_search(5, tables, target, mask, inbits, rng)
-        f7, r7, _ = S.ref_search(7, tables, target, mask, inbits, rng)
-    else:
-        f5, r5, _ = S.oracle_search(5, tables, target, mask, inbits, rng)
-        f7, r7, _ = S.oracle_search(7, tables, target, mask, inbits, rng)
-    dt = time.perf_counter() - t0
-    # Unit accounting (outside the timed region) with the oracle's counters: same semantics.
-    _, _, s5 = S.oracle_search(5, tables, target, mask, inbits, S.OrcRng.from_seed(seed))
-    lst, s7 = S.oracle_filter7(tables, target, mask, inbits)
-    t_units = int(s5.tuples_filtered) + int(s7.tuples_filtered)
-    c_units = int(s5.candidates)
-    if f7:
-        rng2 = S.OrcRng.from_seed(seed)
-        S.oracle_search(5, tables, target, mask, inbits, rng2)
-        _, _, s7b = S.oracle_search(7, tables, target, mask, inbits, rng2)
-        c_units += int(s7b.candidates)
-    else:
-        c_units += len(lst) * C_PER_7
-    return dt, t_units, c_units
+    t_units = c_units = done = 0
+    elapsed = 0.0
+    t_start = time.perf_counter()
+    for tables, target, mask, inbits, seed in samples:
+        rng = S.OrcRng.from_seed(seed)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            f5, r5, _ = S.ref_search(5, tables, target, mask, inbits, rng)
+            f7, r7, _ = S.ref_search(7, tables, target, mask, inbits, rng)
+        else:
+            f5, r5, _ = S.oracle_search(5, tables, target, mask, inbits, rng)
+            f7, r7, _ = S.oracle_search(7, tables, target, mask, inbits, rng)
+        elapsed += time.perf_counter() - t0
+        # Unit accounting (outside the timed region) with the oracle's counters: same semantics.
+        _, _, s5 = S.oracle_search(5, tables, target, mask, inbits, S.OrcRng.from_seed(seed))
+        lst, s7 = S.oracle_filter7(tables, target, mask, inbits)
+        t_units += int(s5.tuples_filtered) + int(s7.tuples_filtered)
+        c_units += int(s5.candidates)
+        if f7:
+            rng2 = S.OrcRng.from_seed(seed)
+            S.oracle_search(5, tables, target, mask, inbits, rng2)
+            _, _, s7b = S.oracle_search(7, tables, target, mask, inbits, rng2)
+            c_units += int(s7b.candidates)
+        else:
+            c_units += len(lst) * C_PER_7
+        done += 1
+        if time.perf_counter() - t_start > deadline_s:
+            break
+    return elapsed, t_units, c_units, done
 
 
 def _pick_sample_gates(state, budget_s):
@@ -242,30 +253,171 @@ def _pick_sample_gates(state, budget_s):
 
 
 def cpu_arm(n, batch, seed, budget_s=12.0, cores=None):
-    """Times the reference (or the oracle port) on a bounded sample, one process per host core."""
+    """Times the reference (or the oracle port) on a bounded sample, one process per host core.
+    Every process works through samples of about budget_s / 4 each until budget_s has passed and
+    reports its own throughput; the arm's value is the sum over the processes (all cores busy for
+    the whole budget, no process waiting for the slowest)."""
     import multiprocessing as mp
     kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsbgref.so")) \
         else "port"
     cores = cores or os.cpu_count() or 1
-    states = build_batch(n, max(batch, cores), seed)
-    jobs = []
+    states = build_batch(n, max(batch, 8), seed)
+    per_sample = max(budget_s / 4.0, 0.05)
+    sized = []
     npr_used = []
-    for i in range(cores):
-        st = states[i % len(states)]
-        npr = _pick_sample_gates(st, budget_s)
+    for st in states:
+        npr = _pick_sample_gates(st, per_sample)
         npr_used.append(npr)
-        jobs.append((kind, st["tables"][:npr].copy(), st["target"], st["mask"],
-                     [b for b in st["inbits"] if b < npr], 77 + i))
+        sized.append((st["tables"][:npr].copy(), st["target"], st["mask"],
+                      [b for b in st["inbits"] if b < npr]))
+    jobs = []
+    for i in range(cores):
+        samples = [sized[(i + k) % len(sized)] + (77 + i * 31 + k,) for k in range(16)]
+        jobs.append((kind, samples, budget_s))
+    t0 = time.perf_counter()
     with mp.get_context("spawn").Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
-    wall = max(r[0] for r in res)
-    t_units = sum(r[1] for r in res)
-    c_units = sum(r[2] for r in res)
-    return {"value": (t_units + c_units) / wall, "unit": UNIT, "cores": cores, "kind": kind,
+    wall = time.perf_counter() - t0
+    t_rate = sum(r[1] / r[0] for r in res if r[0] > 0)
+    c_rate = sum(r[2] / r[0] for r in res if r[0] > 0)
+    busy = max(r[0] for r in res)
+    return {"value": t_rate + c_rate, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": "%d processes, each the reference's search_5lut+search_7lut on the first "
-                      "n'=%s gates of one workload state (n=%d); %.3g T-units + %.3g C-units in %.1f s"
-                      % (cores, sorted(set(npr_used)), n, t_units, c_units, wall),
-            "t_units_per_s": t_units / wall, "c_units_per_s": c_units / wall, "seconds": wall}
+                      "n'=%s gates of workload states (n=%d), one sample after the other for %.1f s; "
+                      "%d samples, %.3g T-units + %.3g C-units; value = sum of the processes' own "
+                      "throughputs" % (cores, sorted(set(npr_used)), n, budget_s,
+                                       sum(r[3] for r in res), sum(r[1] for r in res),
+                                       sum(r[2] for r in res)),
+            "t_units_per_s": t_rate, "c_units_per_s": c_rate, "seconds": busy,
+            "wall_seconds": wall}
+
+
+# ------------------------------------------------------------------------------------------------
+# recorded real calls (tests/golden/run_*.bin; layout: oracle/ref_glue.c, SBGREF_RECORDER)
+
+def read_recorded_calls(path):
+    import struct
+    data = open(path, "rb").read()
+    off, out = 0, []
+    while off < len(data):
+        magic, n = struct.unpack_from("<II", data, off)
+        off += 8
+        which = {0x35474253: 5, 0x37474253: 7}[magic]
+        tables = np.frombuffer(data, dtype="<u8", count=4 * n, offset=off).reshape(n, 4).copy()
+        off += 32 * n
+        target = np.frombuffer(data, dtype="<u8", count=4, offset=off).copy()
+        mask = np.frombuffer(data, dtype="<u8", count=4, offset=off + 32).copy()
+        off += 64
+        inbits = []
+        for b in np.frombuffer(data, dtype=np.int8, count=8, offset=off):   # -1 terminated
+            if b == -1:
+                break
+            inbits.append(int(b))
+        off += 8
+        rng_s = list(struct.unpack_from("<16Q", data, off))
+        off += 128
+        rng_p, found = struct.unpack_from("<II", data, off)
+        off += 8
+        ret = list(struct.unpack_from("<10H", data, off))
+        off += 20
+        draws, ns = struct.unpack_from("<QQ", data, off)
+        off += 16
+        out.append(dict(which=which, tables=tables, target=target, mask=mask, inbits=inbits,
+                        rng_s=rng_s, rng_p=rng_p, found=bool(found), ret=ret, ns=ns))
+    return out
+
+
+def replay_record(eng, sb):
+    """Recorded real calls of seeded reference runs through the C ABI: results must equal the
+    recorded ones (asserted), throughput in the units the reference spent on them."""
+    from sboxgates_b200.rng import Xorshift1024
+    out = {}
+    for name in ("run_rijndael_seed1.bin", "run_sodark_seed1.bin", "run_des_s1_seed1.bin"):
+        path = os.path.join(ROOT, "tests", "golden", name)
+        if not os.path.exists(path) or os.path.getsize(path) == 0:
+            continue
+        calls = read_recorded_calls(path)
+        for c in calls[:3]:   # warm-up
+            fn = sb.search_5lut if c["which"] == 5 else sb.search_7lut
+            fn(eng, c["tables"], c["target"], c["mask"], c["inbits"],
+               Xorshift1024.from_state(c["rng_s"], c["rng_p"]))
+        t_units = c_units = 0
+        t0 = time.perf_counter()
+        for c in calls:
+            fn = sb.search_5lut if c["which"] == 5 else sb.search_7lut
+            r = fn(eng, c["tables"], c["target"], c["mask"], c["inbits"],
+                   Xorshift1024.from_state(c["rng_s"], c["rng_p"]))
+            if (r.found, r.ret) != (c["found"], c["ret"]):
+                raise SystemExit("replay of %s: result differs from the recorded reference call" % name)
+            n = c["tables"].shape[0]
+            if c["which"] == 5:
+                t_units += (int(r.index) + 1) if r.found else math.comb(n, 5)
+                c_units += (r.ordering * 256 + r.pos_outer + 1) if r.found \
+                    else int(r.tuples_feasible) * C_PER_5
+            else:
+                t_units += int(r.tuples_swept)
+                c_units += (int(r.index) * C_PER_7 + r.ordering * 65536 + r.pos_outer * 256
+                            + r.pos_middle + 1) if r.found else int(r.tuples_feasible) * C_PER_7
+        secs = time.perf_counter() - t0
+        ref_secs = sum(c["ns"] for c in calls) * 1e-9
+        out[name] = {"calls": len(calls), "seconds": secs, "us_per_call": 1e6 * secs / len(calls),
+                     "units_per_s": (t_units + c_units) / secs, "t_units": t_units,
+                     "c_units": c_units, "reference_seconds_when_recorded": ref_secs,
+                     "parity": True}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# wall-clock to graph: the drop-in CLI on BASELINE.json configs[1]
+
+def graph_record():
+    """`sboxgates_gpu -l -o 0 rijndael.txt` (the reference's own host code + our shim and library)
+    under the two committed seeds: wall seconds, what the shim reports about itself, the file
+    written, and an independent functional check of that file (sboxgates_b200/graph.py)."""
+    import glob
+    import re
+    import tempfile
+    from sboxgates_b200 import graph as G
+    exe = os.path.join(ROOT, "oracle", "_ref", "sboxgates_gpu")
+    sbox_path = os.path.join(ROOT, "oracle", "_ref", "sboxes", "rijndael.txt")
+    if not (os.path.exists(exe) and os.path.exists(sbox_path)):
+        return {"unavailable": "oracle/_ref/sboxgates_gpu not built (needs /root/reference at build time)"}
+    sbox, _ = G.load_sbox(sbox_path)
+    runs = []
+    for seed in ("seed1", "seed2"):
+        with tempfile.TemporaryDirectory() as tmp:
+            env = dict(os.environ, SBG_SEEDFILE=os.path.join(ROOT, "tests", "golden", seed + ".bin"),
+                       SBG_SHIM_STATS="1")
+            t0 = time.perf_counter()
+            res = subprocess.run([exe, "-l", "-o", "0", sbox_path], cwd=tmp, env=env,
+                                 capture_output=True, text=True, timeout=600)
+            wall = time.perf_counter() - t0
+            files = sorted(os.path.basename(p) for p in glob.glob(os.path.join(tmp, "*.xml")))
+            run = {"seed": seed, "wall_s": wall, "rc": res.returncode, "xml": files[-1] if files else None}
+            if files:
+                g = G.load_graph(os.path.join(tmp, files[-1]))
+                run["verified_output_bits"] = G.verify_graph(g, sbox, require_bits=[0])
+                run["luts"] = g.num_luts
+        m = re.search(r"start-up \(sbg_create\) ([0-9.]+) s", res.stderr)
+        if m:
+            run["startup_s"] = float(m.group(1))
+        m = re.search(r"lut_search: (\d+) calls ([0-9.]+) s \(ended at: 3-LUT (\d+), 5-LUT (\d+), "
+                      r"7-LUT (\d+), nothing (\d+)\)", res.stderr)
+        if m:
+            calls, secs = int(m.group(1)), float(m.group(2))
+            run.update({"lut_search_calls": calls, "lut_search_s": secs,
+                        "us_per_call_without_startup": 1e6 * (secs - run.get("startup_s", 0.0))
+                        / max(calls, 1),
+                        "ended_at": {"lut3": int(m.group(3)), "lut5": int(m.group(4)),
+                                     "lut7": int(m.group(5)), "nothing": int(m.group(6))}})
+        m = re.search(r"(\d+) kernel launches", res.stderr)
+        if m:
+            run["kernel_launches"] = int(m.group(1))
+        runs.append(run)
+    return {"command": "sboxgates_gpu -l -o 0 rijndael.txt (reference host objects + node shim + "
+                       "libsboxgates_b200.so)", "runs": runs,
+            "note": "the reference itself does not finish this configuration in an hour "
+                    "(BASELINE.md section 2)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -279,27 +431,23 @@ def main():
     ap.add_argument("--gates", type=int, default=40)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--shard", default="states", choices=["states", "tuples"],
-                    help="N > 1: states = every rank searches --batch independent states per step "
-                         "(weak scaling); tuples = --batch states in total, every search sharded "
-                         "over the tuple space (strong scaling)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="only the headline measurement (no sharded / graph / replay records)")
+    ap.add_argument("--sharded-gates", default="96,128",
+                    help="state sizes of the tuple-space sharding record")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    by_states = world > 1 and args.shard == "states"
-    n_states = args.batch * world if by_states else args.batch
-    scaling = "weak" if by_states or world == 1 else "strong"
+    n_states = args.batch * world
     config = {"workload": "rijndael.txt --lut -o 0 shaped: %d states/step, n=%d gates, target = "
                           "S-box bit 0, mux masks of depth 0-3, full no-match sweeps of "
                           "search_5lut+search_7lut" % (n_states, args.gates),
               "gates": args.gates, "states_per_step": n_states, "states_per_gpu": args.batch,
               "parallelism": "1 GPU" if world == 1 else (
-                  "%d ranks x %d independent search states per step "
-                  "(one all-gather of the result keys per step)" % (world, args.batch) if by_states else
-                  "%d ranks; every search sharded over the tuple space (all-gather of hit lists + "
-                  "all-reduce(MIN) per phase above the size thresholds, replicated below)" % world),
+                  "%d ranks x %d independent search states per step; result keys exchanged with one "
+                  "non-blocking all-gather per step" % (world, args.batch)),
               "l2": "a 256 MiB buffer is overwritten between steps (L2 flush); every step uses new states"}
 
     if args.impl == "reference":
@@ -312,7 +460,7 @@ def main():
         best = max(vals, key=lambda v: v["value"])
         line = {"impl": "reference", "metric": METRIC, "value": best["value"], "unit": UNIT,
                 "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
-                "ms_per_step": 1e3 * best["seconds"], "higher_is_better": True, "scaling": scaling,
+                "ms_per_step": 1e3 * best["seconds"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32 bitwise", "data": "synthetic", "config": config,
                 "cpu_baseline": best,
                 "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
@@ -332,7 +480,6 @@ def main():
     eng = sb.LutEngine(local_rank)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
-    drv = DistributedLutSearch(eng) if world > 1 and not by_states else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -341,62 +488,54 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    n, B = args.gates, n_states
+    n, B = args.gates, args.batch
     total_steps = args.warmup + args.steps
-    batches = [build_batch(n, B, 1000 + s) for s in range(total_steps)]
+    # this rank's states of every step: rank r takes states r*B .. r*B+B-1 of the step's n_states
+    batches = [build_batch(n, n_states, 1000 + s)[rank * B:(rank + 1) * B] for s in range(total_steps)]
 
-    def run_step(states, resident, acc):
-        """One step.  resident=True: states are already staged in HBM slots (value);
-        False: host tables go through sbg_load_problem inside the step (e2e)."""
-        keys = []
+    def jobs_of(states):
+        return [dict(slot=i, order5=st["order5"], outer=st["outer"], middle=st["middle"])
+                for i, st in enumerate(states)]
+
+    def stage(states):
         for i, st in enumerate(states):
-            if by_states and i // args.batch != rank:
-                continue          # another rank's state
-            if resident:
-                eng.use(i % args.batch)
-            else:
-                eng.load(st["tables"], st["target"], st["mask"], st["inbits"])
-            if drv is None:
-                r5 = eng.search5(st["order5"])
-                k5 = eng.kernel_ms(0)
-                r7 = eng.search7(st["outer"], st["middle"])
-            else:
-                r5 = drv.search5_sharded(st["order5"])
-                k5 = eng.kernel_ms(0)
-                r7 = drv.search7_sharded(st["outer"], st["middle"])
-            keys += [int(r5.key) & 0x7FFFFFFFFFFFFFFF, int(r7.key) & 0x7FFFFFFFFFFFFFFF]
+            eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
+
+    pending = []
+
+    def run_step(states, acc, one_by_one=False):
+        """One step: every state's search_5lut followed by search_7lut (lut.c:553,593) -- through
+        ONE sbg_search_batch call (the states' chains overlap on the device), or one state at a time
+        (timing mode: kernel families are timed in isolation)."""
+        if one_by_one:
+            res = [eng.search_batch([j])[0] for j in jobs_of(states)]
+        else:
+            res = eng.search_batch(jobs_of(states))
+        keys = []
+        for r in res:
+            keys += [int(r.r5.key) & 0x7FFFFFFFFFFFFFFF, int(r.r7.key) & 0x7FFFFFFFFFFFFFFF]
             if acc is not None:
-                t5, t7, c = units_of(n, r5, r7)
-                acc["T"] += t5
+                t5, t7, c = units_of(n, r.r5, r.r7)
+                acc["T5"] += t5
+                acc["T7"] += t7
                 acc["C"] += c
-                if drv is None or drv.last_phase1_sharded:
-                    acc["T7"] += t7           # this rank's share (summed over ranks below)
-                else:
-                    acc["T7_rep"] += t7       # phase 1 replicated on every rank: count it once
-                acc["ms5"] += k5
-                acc["ms_filter"] += eng.kernel_ms(1)
-                acc["ms_sort"] += eng.kernel_ms(2)
-                acc["ms_decomp"] += eng.kernel_ms(3)
-        if by_states:
-            # every rank ends the step knowing every state's result, as the host program would
-            per = 2 * ((len(states) + world - 1) // world)
-            mine = torch.full((per,), -1, dtype=torch.int64, device="cuda")
-            mine[:len(keys)] = torch.tensor(keys, dtype=torch.int64)
-            allk = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(allk, mine)
+        if world > 1:
+            # every rank ends up knowing every state's result, as the host program would; the
+            # exchange does not hold up the next step (its states are independent)
+            mine = torch.tensor(keys, dtype=torch.int64).cuda(non_blocking=True)
+            allk = torch.empty(world * len(keys), dtype=torch.int64, device="cuda")
+            pending.append((dist.all_gather_into_tensor(allk, mine, async_op=True), allk, mine))
+        return res
 
     def timed(resident):
-        acc = {"T": 0, "C": 0, "T7": 0, "T7_rep": 0, "ms5": 0.0, "ms_filter": 0.0, "ms_sort": 0.0,
-               "ms_decomp": 0.0}
+        acc = {"T5": 0, "T7": 0, "C": 0}
         sampler = ClockSampler(local_rank)   # samples every 20 ms from the warm-up on
         sampler.start()
         for s in range(args.warmup):
-            if resident:
-                for i, st in enumerate(batches[s]):
-                    if not by_states or i // args.batch == rank:
-                        eng.stage(i % args.batch, st["tables"], st["target"], st["mask"], st["inbits"])
-            run_step(batches[s], resident, None)
+            stage(batches[s])
+            run_step(batches[s], None)
         launches0 = eng.launches
+        tr0 = eng.transfer_stats()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
               for _ in range(args.steps)]
         barrier()
@@ -404,48 +543,70 @@ def main():
         for s in range(args.steps):
             states = batches[args.warmup + s]
             if resident:   # inputs resident in HBM before the timed region of this step starts
-                for i, st in enumerate(states):
-                    if not by_states or i // args.batch == rank:
-                        eng.stage(i % args.batch, st["tables"], st["target"], st["mask"], st["inbits"])
+                stage(states)
             flush.fill_(s & 0xFF)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             ev[s][0].record(stream)
-            run_step(states, resident, acc)
+            if not resident:   # host tables -> device inside the timed region
+                stage(states)
+            run_step(states, acc)
             ev[s][1].record(stream)
             torch.cuda.synchronize()
             t_wall += time.perf_counter() - t0
+        t_gather0 = time.perf_counter()
+        for work, _, _ in pending:
+            work.wait()
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - t_gather0)
+        pending.clear()
         clocks = sampler.stop()
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-        # every search ends with a device->host read of its result, so device time ~ wall time;
-        # report the larger (it includes host-side launch gaps) and take the max over ranks
-        ms = max(dev_ms, 1e3 * t_wall)
+        # results are read from mapped memory while the stream is still draining, so the host's
+        # clock and the stream's events bracket slightly different things: report the larger
+        own_ms = max(dev_ms, 1e3 * t_wall) + gather_ms
+        ranks_ms = [own_ms]
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        acc["T7_local"], acc["ms_filter_local"] = acc["T7"] + acc["T7_rep"], acc["ms_filter"]
-        if world > 1:   # units are produced on different ranks: sum the shares
-            t = torch.tensor([acc["T7"]] + ([acc["T"], acc["C"]] if by_states else [0, 0]),
-                             dtype=torch.int64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            acc["T7"] = int(t[0].item())
-            if by_states:
-                acc["T"], acc["C"] = int(t[1].item()), int(t[2].item())
-            t = torch.tensor([acc["ms_filter"]], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            acc["ms_filter"] = float(t.item())
-        acc["T7"] += acc["T7_rep"]
-        acc["T"] += acc["T7"]
+            t = torch.tensor([own_ms], dtype=torch.float64, device="cuda")
+            allt = torch.empty(world, dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allt, t)
+            ranks_ms = allt.tolist()
+            u = torch.tensor([acc["T5"], acc["T7"], acc["C"]], dtype=torch.int64, device="cuda")
+            dist.all_reduce(u, op=dist.ReduceOp.SUM)
+            acc["T5"], acc["T7"], acc["C"] = (int(x) for x in u.tolist())
         acc["launches"] = eng.launches - launches0
-        return ms, acc, clocks
+        tr1 = eng.transfer_stats()
+        acc["h2d"], acc["d2h"] = tr1[0] - tr0[0], tr1[1] - tr0[1]
+        acc["gather_ms"] = gather_ms
+        return max(ranks_ms), ranks_ms, acc, clocks
 
-    ms_res, acc_res, clocks = timed(resident=True)
-    ms_e2e, acc_e2e, _ = timed(resident=False)
+    ms_res, ranks_res, acc_res, clocks = timed(resident=True)
+    ms_e2e, ranks_e2e, acc_e2e, _ = timed(resident=False)
 
+    # kernel families in isolation (one state at a time, CUDA events between the kernels): the
+    # dominant kernel's launch durations for the roofline; not part of `value`
+    eng.set_timing(True)
+    fam = {"ms5": 0.0, "ms_filter": 0.0, "ms_order": 0.0, "ms_decomp": 0.0}
+    t7_iso = 0
+    for s in range(args.steps):
+        states = batches[args.warmup + s]
+        stage(states)
+        flush.fill_(s & 0xFF)
+        torch.cuda.synchronize()
+        for j in jobs_of(states):
+            r = eng.search_batch([j])[0]
+            t7_iso += int(r.r7.tuples_swept)
+            for k, w in (("ms5", 0), ("ms_filter", 1), ("ms_order", 2), ("ms_decomp", 3)):
+                fam[k] += eng.kernel_ms(w)
+    eng.set_timing(False)
+    alu_peak = eng.alu_peak()
+
+    extras = {}
+    if not args.no_extras:
+        extras["sharded"] = sharded_record(eng, sb, DistributedLutSearch, args, rank, world)
     if rank == 0:
-        units = acc_res["T"] + acc_res["C"]
+        units = acc_res["T5"] + acc_res["T7"] + acc_res["C"]
         value = units / (ms_res * 1e-3)
         peaks = {}
         try:
@@ -453,59 +614,168 @@ def main():
         except OSError:
             pass
         peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-        # dominant kernel: the 7-LUT phase-1 sweep, one launch per state per step
-        # (per GPU: this rank's launches and the combinations they swept)
-        filt_s = acc_res["ms_filter_local"] * 1e-3
-        achieved = acc_res["T7_local"] * BYTES_T7 / max(filt_s, 1e-12) / 1e9
-        dram_per_launch = None
+        filt_s = fam["ms_filter"] * 1e-3
+        hbm_equiv = t7_iso * BYTES_T7 / max(filt_s, 1e-12) / 1e9
+        # warp instructions of the dominant kernel: counted by ncu on these very states
+        # (scripts/ncu_inst_counts.sh writes the table; see profiles/README.md)
+        inst = None
+        inst_src = os.path.join(ROOT, "profiles", "r02_filter_inst_counts.json")
         try:
-            dram_per_launch = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[
+            tab = json.load(open(inst_src))
+            if tab.get("gates") == n and tab.get("batch") == B:
+                per_step = [tab["per_step_seed"].get(str(1000 + args.warmup + s)) for s in range(args.steps)]
+                if all(p is not None for p in per_step):
+                    inst = float(sum(sum(p) for p in per_step))
+        except (OSError, ValueError, KeyError):
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))[
                 "filter7_bytes_per_launch"]
         except (OSError, KeyError, ValueError):
             pass
+        launches_filter = args.steps * B
+        roofline = {
+            "bound": "alu", "kernel": "k_filter7_pm<NW,W,P,FS,SH> (search_7lut phase 1)",
+            "unit": "warp-instr/s", "peak": alu_peak,
+            "peak_source": "LOP3 issue rate measured in this run (sbg_alu_peak: 8 dependent chains "
+                           "per thread, 8 CTAs per SM)",
+            "achieved": (inst / filt_s) if inst else None,
+            "frac": (inst / filt_s / alu_peak) if inst and alu_peak > 0 else None,
+            "warp_instructions": inst, "launches": launches_filter,
+            "avg_launch_ms": fam["ms_filter"] / max(launches_filter, 1),
+            "instruction_count_source": "profiles/r02_filter_inst_counts.json (ncu "
+                                        "smsp__inst_executed.sum on the same states)" if inst else
+                                        "missing: run scripts/ncu_inst_counts.sh",
+            "traffic": traffic,
+            "note": "no contraction in this path and 16.5 KB of operands per search served from "
+                    "shared memory: the binding resource is integer-ALU issue, not HBM or tensor "
+                    "cores (SURVEY.md 8d); launch durations are CUDA-event times of the kernel "
+                    "running alone",
+        }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "u32 bitwise (LOP3)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitwise (LOP3)",
             "data": "synthetic", "config": config,
-            "t_units_per_s": acc_res["T"] / (ms_res * 1e-3),
+            "t_units_per_s": (acc_res["T5"] + acc_res["T7"]) / (ms_res * 1e-3),
             "c_units_per_s": acc_res["C"] / (ms_res * 1e-3),
-            "units_per_step": {"T": acc_res["T"] // args.steps, "C": acc_res["C"] // args.steps},
-            "kernel_ms_per_step": {k: acc_res[k] / args.steps
-                                   for k in ("ms5", "ms_filter", "ms_sort", "ms_decomp")},
-            "e2e": {"value": (acc_e2e["T"] + acc_e2e["C"]) / (ms_e2e * 1e-3), "unit": UNIT,
-                    "ms_per_step": ms_e2e / args.steps,
-                    # per state: problem block (compressed tables, target, mask; the position-major
-                    # copy is derived on the device), 5-LUT position table and the two 7-LUT
-                    # position tables (kernel arguments)
-                    "h2d_bytes_per_step": B * (16464 + 256 + 512),
-                    # per state: control words after search_5lut; 128-byte header + first 1,024 list
-                    # entries after search_7lut
-                    "d2h_bytes_per_step": B * (72 + 128 + 8192),
-                    "note": "host tables -> sbg_load_problem -> sbg_search5/7 -> result structs"},
+            "units_per_step": {"T": (acc_res["T5"] + acc_res["T7"]) // args.steps,
+                               "C": acc_res["C"] // args.steps},
+            "per_rank_ms_per_step": {"min": min(ranks_res) / args.steps,
+                                     "mean": sum(ranks_res) / len(ranks_res) / args.steps,
+                                     "max": max(ranks_res) / args.steps,
+                                     "all_gather_wait_ms_total": acc_res["gather_ms"]},
+            "kernel_ms_per_step_isolated": {k: v / args.steps for k, v in fam.items()},
+            "kernel_to_step_ratio": sum(fam.values()) / ms_res if world == 1 else None,
+            "e2e": {"value": (acc_e2e["T5"] + acc_e2e["T7"] + acc_e2e["C"]) / (ms_e2e * 1e-3),
+                    "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    # counted by the library: gate tables, targets and masks shipped (kernel
+                    # arguments or copies) / result blocks read from mapped memory
+                    "h2d_bytes_per_step": acc_e2e["h2d"] // args.steps,
+                    "d2h_bytes_per_step": acc_e2e["d2h"] // args.steps,
+                    "note": "host tables -> sbg_stage_problem -> sbg_search_batch -> result structs"},
             "gpu_launches": acc_res["launches"],
-            "roofline": {
-                "bound": "hbm", "kernel": "k_filter7_pm<NW,W,P> (search_7lut phase 1)",
-                "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+            "roofline": roofline,
+            "roofline_hbm_equiv": {
+                "bound": "hbm", "achieved": hbm_equiv, "peak": peak_gbs, "unit": "GB/s",
+                "frac": hbm_equiv / peak_gbs,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "traffic": dram_per_launch,
-                "note": "algorithmic bytes = 224 B per 7-combination (SURVEY.md 8d); operands are "
-                        "served from shared memory, compulsory DRAM traffic is the problem block (31-50 KB "
-                        "per launch, ncu), so frac > 1 is expected; the binding resource is integer-ALU "
-                        "issue (57-71 % of that pipe's measured peak, ncu capture F), see profiles/ and "
-                        "DESIGN.md",
-            },
+                "note": "SURVEY.md 8d unit conversion: 224 algorithmic bytes per 7-combination / "
+                        "kernel time; operands never leave shared memory, so this is not a memory "
+                        "utilisation and exceeds 1"},
             "clocks": clocks,
         }
+        line.update(extras)
+        if not args.no_extras and world == 1:
+            line["replay"] = replay_record(eng, sb)
+        eng.close()
+        if not args.no_extras and world == 1:
+            line["graph"] = graph_record()
         if not args.no_cpu_baseline and world == 1:
             try:
                 line["cpu_baseline"] = cpu_arm(n, B, 2000, budget_s=12.0)
             except Exception as exc:  # keep the GPU line even if the CPU leg cannot run
                 line["cpu_baseline"] = {"error": repr(exc)}
         print(json.dumps(line))
-    eng.close()
+    else:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_record(eng, sb, DistributedLutSearch, args, rank, world):
+    """north_star's partition: ONE search sharded over the ranks' GPUs -- work items dealt
+    round-robin, the 7-LUT hit lists all-gathered and merged on the devices, one all-reduce(MIN) of
+    the key per phase (replacing lut.c:137-149, 329-360, 665-740).  Large states, full-mask
+    no-match sweeps.  Parity is asserted in the run: the sharded result and list must equal the
+    unsharded ones computed on rank 0's GPU alone."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    rec = {}
+    target = _rijndael_bit(0)
+    full = np.full(4, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    for n in [int(x) for x in args.sharded_gates.split(",") if x]:
+        tabs = _state(n, 4242 + n)
+        rs = np.random.RandomState(n)
+        o5, oo, om = _orders(rs)
+        eng.load(tabs, target, full, [])
+
+        def sync():
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+
+        # unsharded, one GPU (every rank does it: the ranks stay in step and it warms the caches)
+        sync()
+        t0 = time.perf_counter()
+        r5 = eng.search5(o5)
+        r7 = eng.search7(oo, om)
+        torch.cuda.synchronize()
+        ms_one = 1e3 * (time.perf_counter() - t0)
+        one = (int(r5.key), int(r7.key), int(r7.tuples_feasible))
+        lst = eng.filter7_part(0, 1)
+        list_hash = hashlib.sha1(lst.tobytes()).hexdigest()
+        entry = {"gates": n, "t_units": math.comb(n, 5) + math.comb(n, 7),
+                 "ms_one_gpu": ms_one, "list_len": len(lst)}
+        if world > 1:
+            drv = DistributedLutSearch(eng, shard_min_tuples5=0, shard_min_tuples7=0, shard_min_list=0)
+            eng.load(tabs, target, full, [])
+            sync()
+            c0 = drv.collectives
+            t0 = time.perf_counter()
+            s5 = drv.search5_sharded(o5)
+            s7 = drv.search7_sharded(oo, om)
+            torch.cuda.synchronize()
+            own = 1e3 * (time.perf_counter() - t0)
+            t = torch.tensor([own], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            got = (int(s5.key), int(s7.key), int(s7.tuples_feasible))
+            # the merged list every rank ended up with
+            ptr, cnt = eng.list7_device()
+            merged = torch.as_tensor(sb.distributed._DeviceArray(ptr, cnt), device="cuda").cpu().numpy() \
+                if cnt else np.zeros(0, dtype=np.int64)
+            merged_hash = hashlib.sha1(merged.view(np.uint64).tobytes()).hexdigest()
+            ok = got == one and merged_hash == list_hash
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) != 1:
+                raise SystemExit("sharded search differs from the unsharded one: n=%d rank=%d %r vs %r"
+                                 % (n, rank, got, one))
+            entry.update({"ms": ms, "collectives": drv.collectives - c0,
+                          "collective_ms": drv.collective_ms, "parity": True,
+                          "strong_scaling_vs_one_gpu": ms_one / ms})
+        else:
+            entry.update({"ms": ms_one, "collectives": 0, "collective_ms": 0.0, "parity": True})
+        entry["t_units_per_s"] = entry["t_units"] / (entry["ms"] * 1e-3)
+        rec["n%d" % n] = entry
+    rec["what"] = ("one state per size, full mask, search_5lut + search_7lut of that state sharded over "
+                   "the tuple space across all ranks (ms = max over ranks); ms_one_gpu = the same "
+                   "search on one GPU in the same run; parity = keys and merged hit list identical")
+    return rec
 
 
 if __name__ == "__main__":

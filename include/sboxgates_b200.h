@@ -180,6 +180,12 @@ int sbg_set_list7(sbg_handle *h, const uint64_t *list, int count);
 int sbg_list7_device(sbg_handle *h, const uint64_t **list, int *count);
 int sbg_set_list7_device(sbg_handle *h, const uint64_t *runs, uint64_t stride, const int *counts,
     int nruns);
+/* One process driving several devices (handles hs[0..nh-1], one per device, each holding its part's
+   ordered list from sbg_filter7_part(part = i, nparts = nh)): gathers every part's list onto every
+   device (peer copies over NVLink) and merges them there; afterwards every handle has the same
+   installed list.  *total = its length.  The in-process counterpart of the all-gather
+   (lut.c:329-349). */
+int sbg_allgather_merge7(sbg_handle *const *hs, int nh, int *total);
 /* 7-LUT phase 2 over list indices congruent to part modulo nparts. */
 int sbg_decomp7_part(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
     const uint8_t *middle_order, uint64_t *key);

@@ -121,6 +121,17 @@ int sbgref_sizes(int *sz_ttable, int *sz_gate, int *sz_state, int *off_gates) {
   return 0;
 }
 
+/* sboxgates.h:49-66, boolfunc.h:28-40: what the node-level shim assumes about `options`. */
+int sbgref_options_layout(int *off_randomize, int *off_lut_graph, int *off_verbosity, int *sz_options,
+    int *sz_boolfunc) {
+  *off_randomize = (int)__builtin_offsetof(options, randomize);
+  *off_lut_graph = (int)__builtin_offsetof(options, lut_graph);
+  *off_verbosity = (int)__builtin_offsetof(options, verbosity);
+  *sz_options = (int)sizeof(options);
+  *sz_boolfunc = (int)sizeof(boolfunc);
+  return 0;
+}
+
 int sbgref_check_n_lut_possible(int num, const uint64_t *target, const uint64_t *mask,
     const uint64_t *tables /* num x 4 */) {
   ttable tt[7];

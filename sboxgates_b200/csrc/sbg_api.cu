@@ -1809,6 +1809,53 @@ int sbg_set_list7(sbg_handle *h, const uint64_t *list, int count) {
   return sbg_set_list7_device(h, L.d_hits, stride, counts, nruns);
 }
 
+int sbg_allgather_merge7(sbg_handle *const *hs, int nh, int *total) {
+  if (hs == nullptr || nh < 1 || nh > kMaxRuns || total == nullptr) return SBG_ERR_ARG;
+  int counts[kMaxRuns];
+  uint64_t stride = 1;
+  *total = 0;
+  for (int i = 0; i < nh; i++) {
+    if (hs[i] == nullptr) return SBG_ERR_ARG;
+    counts[i] = (int)hs[i]->lane[0].list_count;
+    stride = std::max<uint64_t>(stride, (uint64_t)counts[i]);
+    *total += counts[i];
+  }
+  *total = std::min(*total, SBG_LIST_CAP);
+  // 1. every device pulls every part's list into its staging area (d_aux); the lists are complete
+  //    (sbg_filter7_part returns after its device finished)
+  for (int d = 0; d < nh; d++) {
+    sbg_handle *h = hs[d];
+    sbg_lane &L = h->lane[0];
+    SBG_CUDA(h, cudaSetDevice(h->device));
+    int rc = ensure_hits(h, L, std::max<size_t>(std::max(L.hits_cap, h->hits_cap_default),
+        (size_t)nh * stride));
+    if (rc != SBG_OK) return rc;
+    for (int s = 0; s < nh; s++) {
+      if (counts[s] == 0) continue;
+      if (hs[s]->device != h->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, h->device, hs[s]->device);
+        if (can) {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(hs[s]->device, 0);
+          if (e != cudaSuccess) (void)cudaGetLastError();   // already enabled
+        }
+      }
+      SBG_CUDA(h, cudaMemcpyPeerAsync(L.d_aux + (uint64_t)s * stride, h->device,
+          hs[s]->lane[0].d_sorted, hs[s]->device, (size_t)counts[s] * sizeof(uint64_t), L.stream));
+    }
+  }
+  // 2. only when every copy has landed may a device overwrite its own list with the merged one
+  for (int d = 0; d < nh; d++) {
+    SBG_CUDA(hs[d], cudaSetDevice(hs[d]->device));
+    SBG_CUDA(hs[d], cudaStreamSynchronize(hs[d]->lane[0].stream));
+  }
+  for (int d = 0; d < nh; d++) {
+    int rc = sbg_set_list7_device(hs[d], hs[d]->lane[0].d_aux, stride, counts, nh);
+    if (rc != SBG_OK) return rc;
+  }
+  return SBG_OK;
+}
+
 int sbg_decomp7_part(sbg_handle *h, int part, int nparts, const uint8_t *outer_order,
     const uint8_t *middle_order, uint64_t *key) {
   if (h == nullptr || key == nullptr) return SBG_ERR_ARG;

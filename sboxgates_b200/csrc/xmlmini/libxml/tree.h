@@ -1,4 +1,4 @@
-/* oracle/stubs/libxml/tree.h -- TEST INFRASTRUCTURE, not product code.
+/* xmlmini/libxml/tree.h -- part of the libxml2-free reader of the drop-in build (see ../xml_mini.c).
  * Minimal stand-in for libxml2's DOM types (libxml2 is not installed in this image).  Only the
  * members the reference touches are present (state.c:260-411: doc->children, node->name,
  * node->children, node->next, xmlGetProp, xmlFree, xmlFreeDoc).  Implemented in ../xml_mini.c.

@@ -1,10 +1,13 @@
-/* oracle/stubs/xml_mini.c -- TEST INFRASTRUCTURE, not product code.
+/* xmlmini/xml_mini.c -- a libxml2-free XML reader for the drop-in build.
  *
- * A tiny XML reader that is just enough for files following the reference's gates.xsd
- * (written by state.c:127-165): an optional <?xml ...?> declaration, comments, and nested elements
- * with double- or single-quoted attributes; text content is ignored.  It exists so that the
- * reference's load_state() (state.c:260-411) -- and with it --graph, -c and -d -- works in the
- * oracle build without libxml2.
+ * The reference needs libxml2 only to READ saved graphs (load_state, state.c:260-411, behind
+ * --graph, -c and -d); it writes them with fprintf.  This file implements the five libxml2 entry
+ * points state.c uses -- xmlParseFile, xmlGetProp, xmlFreeDoc, xmlFree, the node fields name /
+ * children / next -- for files following gates.xsd: an optional <?xml ...?> declaration,
+ * comments, nested elements with double- or single-quoted attributes; text content is ignored.
+ * Linked into the GPU drop-in CLI (and into the reference build the oracle uses) so that loading
+ * a partial graph, DOT and C output work where libxml2 is not installed.  The Python-side
+ * counterpart with the same checks is sboxgates_b200/graph.py.
  */
 #include <ctype.h>
 #include <stdio.h>

@@ -14,6 +14,7 @@ The engine is any object with the `LutEngine` part-methods; the CPU tests drive 
 `gloo` with an oracle-backed stand-in engine, the product uses `LutEngine` (CUDA) over `nccl`.
 """
 import math
+import time
 
 import numpy as np
 import torch
@@ -32,6 +33,14 @@ def _key_to_i64(key):
 
 def _i64_to_key(v):
     return SBG_KEY_NONE if v == _I64_MAX else int(v)
+
+
+class _DeviceArray:
+    """A raw device pointer as something torch can wrap without a copy."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (ptr, False),
+                                         "version": 2}
 
 
 class DistributedLutSearch:
@@ -53,17 +62,22 @@ class DistributedLutSearch:
                 else torch.device("cpu")
         self.device = device
         self.collectives = 0
+        self.collective_ms = 0.0      # host time spent inside collectives (incl. waiting for peers)
         self.last_phase1_sharded = False
 
     # -- collectives ---------------------------------------------------------------------------
     def _allreduce_min_key(self, key):
+        t0 = time.perf_counter()
         t = torch.tensor([_key_to_i64(key)], dtype=torch.int64, device=self.device)
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
         self.collectives += 1
-        return _i64_to_key(int(t.item()))
+        out = _i64_to_key(int(t.item()))
+        self.collective_ms += 1e3 * (time.perf_counter() - t0)
+        return out
 
     def _allgather_lists(self, local):
-        """local: sorted uint64 array (<= SBG_LIST_CAP).  Returns the concatenation over ranks."""
+        """local: sorted uint64 array (<= SBG_LIST_CAP).  Returns the concatenation over ranks.
+        Host path (gloo / engines without a device-side list)."""
         cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=self.device)
         counts = [torch.zeros_like(cnt) for _ in range(self.world)]
         dist.all_gather(counts, cnt, group=self.group)
@@ -81,6 +95,31 @@ class DistributedLutSearch:
         out = [p[:c].cpu().numpy().view(np.uint64) for p, c in zip(parts, counts)]
         return np.concatenate(out)
 
+    def _allgather_merge_on_device(self, count):
+        """NCCL path: every rank's ordered list goes straight from its engine's device buffer into
+        one gathered device buffer (all_gather_into_tensor over NVLink) and is merged there
+        (sbg_set_list7_device); no list ever visits the host.  Returns the merged length."""
+        t0 = time.perf_counter()
+        cnt = torch.tensor([count], dtype=torch.int64, device=self.device)
+        counts = torch.empty(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(counts, cnt, group=self.group)
+        counts = counts.tolist()          # `world` integers: grid sizes are chosen on the host
+        self.collectives += 1
+        width = max(max(counts), 1)
+        mine = torch.zeros(width, dtype=torch.int64, device=self.device)
+        if count > 0:
+            ptr, n = self.engine.list7_device()
+            mine[:count] = torch.as_tensor(_DeviceArray(ptr, n), device=self.device)[:count]
+        gathered = torch.empty(self.world * width, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        self.collectives += 1
+        # the merge kernel runs on the engine's stream, the collective on torch's: order them
+        torch.cuda.current_stream().synchronize()
+        self.collective_ms += 1e3 * (time.perf_counter() - t0)
+        self.engine.set_list7_device(gathered.data_ptr(), width, counts)
+        self._keepalive = gathered
+        return min(sum(counts), SBG_LIST_CAP)
+
     # -- searches ------------------------------------------------------------------------------
     def search5_sharded(self, order):
         """The current problem's 5-LUT search with a given function order -> raw sbg_result."""
@@ -97,10 +136,13 @@ class DistributedLutSearch:
         if not self.last_phase1_sharded:
             # phase 1 replicated: every rank builds (and keeps on its device) the same full list
             count = self.engine.filter7_keep_local()
+        elif self.device.type == "cuda" and hasattr(self.engine, "filter7_part_device"):
+            count = self._allgather_merge_on_device(
+                self.engine.filter7_part_device(self.rank, self.world))
         else:
             local = self.engine.filter7_part(self.rank, self.world)
             merged = self._allgather_lists(local)
-            # Every rank installs the same merged list; set_list7 sorts it and keeps the first
+            # Every rank installs the same merged list: the runs are merged and cut at
             # SBG_LIST_CAP entries (lut.c:316-318 at size == 1).
             self.engine.set_list7(merged)
             count = min(len(merged), SBG_LIST_CAP)

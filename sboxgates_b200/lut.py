@@ -30,6 +30,8 @@ class SearchResult:
     tuples_swept: int = 0
     stale_outer: bool = False
     gates: List[int] = field(default_factory=list)
+    pos_outer: int = 0             # position of func_outer / func_middle in the shuffled orders
+    pos_middle: int = 0
 
 
 def shuffled_order(rng):
@@ -274,6 +276,12 @@ class LutEngine:
                                               out.ctypes.data_as(native.u64p), C.byref(cnt)))
         return out[:cnt.value].copy()
 
+    def filter7_part_device(self, part, nparts):
+        """Phase 1 of this part; the ordered list stays on the device.  Returns its length."""
+        cnt = C.c_int()
+        self._check(self.lib.sbg_filter7_part(self._h, part, nparts, None, C.byref(cnt)))
+        return cnt.value
+
     def filter7_keep_local(self):
         """Phase 1 over the whole space on this device; the sorted, capped list stays in HBM as the
         installed list.  Returns its length."""
@@ -324,7 +332,7 @@ def result5_to_ret(res, rng):
     ret = [res.func_outer, fi] + gates + [0, 0, 0]
     return SearchResult(True, ret, ordering=res.ordering, key=int(res.key), index=int(res.index),
                         tuples_feasible=int(res.tuples_feasible),
-                        tuples_swept=int(res.tuples_swept), gates=gates)
+                        tuples_swept=int(res.tuples_swept), gates=gates, pos_outer=int(res.pos_outer))
 
 
 def result7_to_ret(res, rng):
@@ -340,7 +348,7 @@ def result7_to_ret(res, rng):
     return SearchResult(True, ret, ordering=res.ordering, key=int(res.key), index=int(res.index),
                         tuples_feasible=int(res.tuples_feasible),
                         tuples_swept=int(res.tuples_swept), stale_outer=bool(res.stale_outer),
-                        gates=gates)
+                        gates=gates, pos_outer=int(res.pos_outer), pos_middle=int(res.pos_middle))
 
 
 def search_5lut(engine, tables, target, mask, inbits, rng):
@@ -410,6 +418,8 @@ def lut_search(engine, tables, target, mask, inbits, gate_order, rng, allow5=Tru
         rng.next()
     if node.found_stage == 7:
         r = result7_to_ret(node.r7, rng).ret
-        return LutSearchResult(7, [(r[0], r[3], r[4], r[5]), (r[1], r[6], r[7], r[8]),
-                                   (r[2], ("new", 0), ("new", 1), r[9])], node)
+        # lut.c:622-624 nests the outer and middle add_lut calls as arguments of the third; gcc
+        # evaluates them right to left, so the MIDDLE LUT is added first (lower gate number)
+        return LutSearchResult(7, [(r[1], r[6], r[7], r[8]), (r[0], r[3], r[4], r[5]),
+                                   (r[2], ("new", 1), ("new", 0), r[9])], node)
     return LutSearchResult(0, [], node)

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sbg_search_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SbgJob),
                                    C.POINTER(SbgNodeResult)]),
     "sbg_list7_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "sbg_allgather_merge7": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int)]),
     "sbg_set_list7_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int),
                                        C.c_int]),
     "sbg_load_problem": (C.c_int, [C.c_void_p, u64p, C.c_int, u64p, u64p, i8p]),

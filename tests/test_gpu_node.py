@@ -81,8 +81,9 @@ def test_node_call_matches_reference_stages(engine):
             assert [got.luts[0][0], got.luts[1][0]] + list(got.luts[0][1:]) + list(got.luts[1][2:]) \
                 == want[:7]
         elif want_stage == 7:
-            assert [got.luts[0][0], got.luts[1][0], got.luts[2][0]] + list(got.luts[0][1:]) \
-                + list(got.luts[1][1:]) + [got.luts[2][3]] == want
+            # luts = [middle, outer, inner] (the order the reference binary adds them in)
+            assert [got.luts[1][0], got.luts[0][0], got.luts[2][0]] + list(got.luts[1][1:]) \
+                + list(got.luts[0][1:]) + [got.luts[2][3]] == want
         stages[want_stage] += 1
     assert stages[3] > 5 and stages[5] > 5 and (stages[7] + stages[0]) > 5, stages
 
@@ -223,3 +224,43 @@ def test_device_side_merge_of_part_lists(engine):
                                            ctypes.c_size_t(8 * cnt), 3)
     assert np.array_equal(got.cpu().numpy().view(np.uint64), whole)
     assert engine.decomp7_part(0, 1, outer, middle) == k_host
+
+
+def test_scan3_on_recorded_reference_states(engine):
+    """Every recorded search_5lut call of a reference run comes from a lut_search whose 3-LUT scan
+    had just failed (lut.c:501-523 precedes lut.c:553): the device scan must find nothing on those
+    states either, whatever the gate order -- and, on the same states with a target that some triple
+    does realise, it must return the first such triple of the given order (checked against the CPU
+    oracle's check_n_lut_possible)."""
+    rs = np.random.RandomState(7)
+    recs = [r for r in S.read_records(os.path.join(S.GOLDEN, "run_rijndael_seed1.bin")) if r.which == 5]
+    recs += [r for r in S.read_records(os.path.join(S.GOLDEN, "run_sodark_seed1.bin")) if r.which == 5]
+    assert len(recs) > 100
+    planted = 0
+    for idx, rec in enumerate(recs):
+        n = rec.n
+        order = [int(x) for x in rs.permutation(n)]
+        engine.load(rec.tables, rec.target, rec.mask, rec.inbits_list())
+        node = engine.search_node(0, gate_order=order)
+        assert node.found_stage == 0, (idx, n, list(node.gates3))
+        if idx % 4 == 0:
+            g = [int(x) for x in rs.choice(n, 3, replace=False)]
+            tgt = S.lut_table(int(rs.randint(1, 255)), rec.tables[g[0]], rec.tables[g[1]],
+                              rec.tables[g[2]])
+            engine.load(rec.tables, tgt, rec.mask, rec.inbits_list())
+            node = engine.search_node(0, gate_order=order)
+            want = None
+            for i in range(n):
+                for k in range(i + 1, n):
+                    for m in range(k + 1, n):
+                        if want is None and S.oracle_check(3, tgt, rec.mask, [
+                                rec.tables[order[i]], rec.tables[order[k]], rec.tables[order[m]]]):
+                            want = (order[i], order[k], order[m])
+                    if want:
+                        break
+                if want:
+                    break
+            assert want is not None and node.found_stage == 3
+            assert tuple(int(x) for x in node.gates3) == want, (idx, n)
+            planted += 1
+    assert planted > 20

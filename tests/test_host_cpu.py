@@ -126,3 +126,35 @@ def test_ticket_plan_covers_the_allowed_prefixes_in_order():
             below = list(itertools.islice(itertools.combinations(range(universe), pg), rank))
             assert sum(1 for c in below if all(g in allowed_gates for g in c)) == covered
     assert lib.sbg_plan_tickets(6, 4, 30, 0, 1, 1, out) != 0
+
+
+def test_graph_loader_and_verifier(tmp_path):
+    """sboxgates_b200/graph.py: gates.xsd loader (the checks of state.c:260-411) + functional check."""
+    from sboxgates_b200 import graph as G
+    # 3-input "S-box" whose bit 0 is majority(a, b, c) and bit 1 is a ^ b
+    sbox = [0] * 256
+    for p in range(8):
+        a, b, c = p & 1, (p >> 1) & 1, (p >> 2) & 1
+        sbox[p] = (1 if a + b + c >= 2 else 0) | ((a ^ b) << 1)
+    good = tmp_path / "g.xml"
+    good.write_text(
+        '<?xml version="1.0" encoding="UTF-8" ?>\n<gates>\n'
+        '  <output bit="0" gate="3" />\n  <output bit="1" gate="4" />\n'
+        '  <gate type="IN" />\n  <gate type="IN" />\n  <gate type="IN" />\n'
+        '  <gate type="LUT" function="e8">\n    <input gate="2" />\n    <input gate="1" />\n'
+        '    <input gate="0" />\n  </gate>\n'
+        '  <gate type="XOR">\n    <input gate="0" />\n    <input gate="1" />\n  </gate>\n'
+        '</gates>\n')
+    g = G.load_graph(str(good))
+    assert (g.num_inputs, g.num_luts, g.outputs) == (3, 1, {0: 3, 1: 4})
+    assert G.verify_graph(g, sbox, require_bits=[0, 1]) == [0, 1]
+    sbox_bad = list(sbox)
+    sbox_bad[5] ^= 1
+    import pytest
+    with pytest.raises(G.GraphError):
+        G.verify_graph(g, sbox_bad)
+    bad = tmp_path / "b.xml"
+    bad.write_text('<gates>\n  <gate type="IN" />\n  <gate type="AND">\n    <input gate="0" />\n'
+                   '    <input gate="3" />\n  </gate>\n</gates>\n')
+    with pytest.raises(G.GraphError):
+        G.load_graph(str(bad))

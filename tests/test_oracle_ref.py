@@ -21,6 +21,10 @@ def test_struct_layout_the_shim_assumes():
     a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
     lib.sbgref_sizes(C.byref(a), C.byref(b), C.byref(c), C.byref(d))
     assert (a.value, b.value, c.value, d.value) == (32, 64, 32032, 32)   # state.h:64-88
+    # the node-level shim (lut_search) also reads three fields of `options` (sboxgates.h:49-66)
+    e = C.c_int()
+    lib.sbgref_options_layout(C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(e))
+    assert (a.value, b.value, c.value, d.value, e.value) == (2019, 2018, 9756, 9760, 24)
 
 
 def test_oracle_equals_reference_on_random_cases():
@@ -65,7 +69,7 @@ def test_rijndael_table_is_the_aes_sbox():
 
 def test_saved_graph_loads_back_and_converts():
     """The XML the reference writes is read back by its own loader through our mini XML reader
-    (oracle/stubs/xml_mini.c) and converts to DOT -- exercises --graph/-d in the oracle build."""
+    (sboxgates_b200/csrc/xmlmini) and converts to DOT -- exercises --graph/-d in the oracle build."""
     with tempfile.TemporaryDirectory() as tmp:
         env = dict(os.environ, SBG_SEEDFILE=os.path.join(S.GOLDEN, "seed1.bin"))
         exe = os.path.join(S.REF_DIR, "sboxgates_ref")
@@ -75,3 +79,16 @@ def test_saved_graph_loads_back_and_converts():
         dot = subprocess.run([exe, "-d", xml], cwd=tmp, env=env, check=True, capture_output=True,
                              text=True).stdout
         assert "digraph sbox" in dot and "-> gt" in dot
+        # the Python loader (sboxgates_b200/graph.py) reads the reference's own file and confirms
+        # the circuit, and a 2-input-gate graph (no --lut) as well
+        from sboxgates_b200 import graph as G
+        sbox, _ = G.load_sbox(os.path.join(S.REF_DIR, "sboxes", "crypto1_fc.txt"))
+        g = G.load_graph(xml)
+        assert G.verify_graph(g, sbox, require_bits=[0]) == [0]
+        assert g.num_luts == int(os.path.basename(xml).split("-")[1])
+    with tempfile.TemporaryDirectory() as tmp:
+        subprocess.run([exe, "-o", "0", os.path.join(S.REF_DIR, "sboxes", "des_s1.txt")], cwd=tmp,
+                       env=env, check=True, stdout=subprocess.DEVNULL, timeout=300)
+        xml = sorted(glob.glob(os.path.join(tmp, "*.xml")))[-1]
+        sbox, _ = G.load_sbox(os.path.join(S.REF_DIR, "sboxes", "des_s1.txt"))
+        assert G.verify_graph(G.load_graph(xml), sbox, require_bits=[0]) == [0]
