@@ -19,7 +19,7 @@ a per-tuple summary.  value = (T + C) / s; both are also reported separately.
 N > 1 (torchrun, one rank per GPU): the search states of a step are independent (in the program
 they are the 16 mux branches of create_circuit, the 8 output bits of -o -1 and the -i iterations),
 so every rank takes `--batch` states of a step of N x `--batch` -- its own sbg_search_batch call --
-and the ranks exchange only the result keys (one non-blocking all-gather per step): weak scaling.
+and the ranks exchange only the result keys (one all-gather, inside the timed region): weak scaling.
 The same line carries a `sharded` record: ONE search of a large state (n = 96, 128) sharded over the
 ranks' GPUs across the tuple space (work items dealt round-robin; the 7-LUT hit lists all-gathered
 and merged on the devices, one all-reduce(MIN) per search phase), with the one-GPU time of the same
@@ -433,8 +433,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="only the headline measurement (no sharded / graph / replay records)")
-    ap.add_argument("--sharded-gates", default="96,128",
-                    help="state sizes of the tuple-space sharding record")
+    ap.add_argument("--sharded-gates", default="64h,96,128",
+                    help="state sizes of the tuple-space sharding record; suffix h = one mux level "
+                         "deep (128 masked positions) instead of the full mask")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -447,7 +448,7 @@ def main():
               "gates": args.gates, "states_per_step": n_states, "states_per_gpu": args.batch,
               "parallelism": "1 GPU" if world == 1 else (
                   "%d ranks x %d independent search states per step; result keys exchanged with one "
-                  "non-blocking all-gather per step" % (world, args.batch)),
+                  "all-gather inside the timed region" % (world, args.batch)),
               "l2": "a 256 MiB buffer is overwritten between steps (L2 flush); every step uses new states"}
 
     if args.impl == "reference":
@@ -501,7 +502,19 @@ def main():
         for i, st in enumerate(states):
             eng.stage(i, st["tables"], st["target"], st["mask"], st["inbits"])
 
-    pending = []
+    step_keys = []
+
+    def exchange_keys():
+        """Every rank ends up knowing every state's result, as the host program would: ONE
+        all-gather of the result keys of all the steps run since the last exchange (the states are
+        independent, nothing needs a result before the end)."""
+        if world > 1 and step_keys:
+            flat = [k for ks in step_keys for k in ks]
+            mine = torch.tensor(flat, dtype=torch.int64).cuda()
+            allk = torch.empty(world * len(flat), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allk, mine)
+            torch.cuda.synchronize()
+        step_keys.clear()
 
     def run_step(states, acc, one_by_one=False):
         """One step: every state's search_5lut followed by search_7lut (lut.c:553,593) -- through
@@ -519,12 +532,7 @@ def main():
                 acc["T5"] += t5
                 acc["T7"] += t7
                 acc["C"] += c
-        if world > 1:
-            # every rank ends up knowing every state's result, as the host program would; the
-            # exchange does not hold up the next step (its states are independent)
-            mine = torch.tensor(keys, dtype=torch.int64).cuda(non_blocking=True)
-            allk = torch.empty(world * len(keys), dtype=torch.int64, device="cuda")
-            pending.append((dist.all_gather_into_tensor(allk, mine, async_op=True), allk, mine))
+        step_keys.append(keys)
         return res
 
     def timed(resident):
@@ -534,6 +542,7 @@ def main():
         for s in range(args.warmup):
             stage(batches[s])
             run_step(batches[s], None)
+        exchange_keys()
         launches0 = eng.launches
         tr0 = eng.transfer_stats()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -555,11 +564,8 @@ def main():
             torch.cuda.synchronize()
             t_wall += time.perf_counter() - t0
         t_gather0 = time.perf_counter()
-        for work, _, _ in pending:
-            work.wait()
-        torch.cuda.synchronize()
+        exchange_keys()
         gather_ms = 1e3 * (time.perf_counter() - t_gather0)
-        pending.clear()
         clocks = sampler.stop()
         barrier()
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
@@ -601,6 +607,7 @@ def main():
                 fam[k] += eng.kernel_ms(w)
     eng.set_timing(False)
     alu_peak = eng.alu_peak()
+    props = torch.cuda.get_device_properties(local_rank)
 
     extras = {}
     if not args.no_extras:
@@ -618,14 +625,15 @@ def main():
         hbm_equiv = t7_iso * BYTES_T7 / max(filt_s, 1e-12) / 1e9
         # warp instructions of the dominant kernel: counted by ncu on these very states
         # (scripts/ncu_inst_counts.sh writes the table; see profiles/README.md)
-        inst = None
+        inst = alu_inst = None
         inst_src = os.path.join(ROOT, "profiles", "r02_filter_inst_counts.json")
         try:
             tab = json.load(open(inst_src))
             if tab.get("gates") == n and tab.get("batch") == B:
-                per_step = [tab["per_step_seed"].get(str(1000 + args.warmup + s)) for s in range(args.steps)]
-                if all(p is not None for p in per_step):
-                    inst = float(sum(sum(p) for p in per_step))
+                seeds = [str(1000 + args.warmup + s) for s in range(args.steps)]
+                if all(k in tab["per_step_seed"] for k in seeds):
+                    inst = float(sum(sum(tab["per_step_seed"][k]) for k in seeds))
+                    alu_inst = float(sum(sum(tab["alu_pipe_inst"][k]) for k in seeds))
         except (OSError, ValueError, KeyError):
             pass
         traffic = None
@@ -635,23 +643,30 @@ def main():
         except (OSError, KeyError, ValueError):
             pass
         launches_filter = args.steps * B
+        issue_peak = 4.0 * props.multi_processor_count * 1e6 * (clocks["sm_mhz"] if clocks else 1965.0)
         roofline = {
             "bound": "alu", "kernel": "k_filter7_pm<NW,W,P,FS,SH> (search_7lut phase 1)",
             "unit": "warp-instr/s", "peak": alu_peak,
-            "peak_source": "LOP3 issue rate measured in this run (sbg_alu_peak: 8 dependent chains "
-                           "per thread, 8 CTAs per SM)",
-            "achieved": (inst / filt_s) if inst else None,
-            "frac": (inst / filt_s / alu_peak) if inst and alu_peak > 0 else None,
-            "warp_instructions": inst, "launches": launches_filter,
+            "peak_source": "integer-ALU pipe: LOP3 issue rate measured in this run (sbg_alu_peak: 8 "
+                           "independent dependent chains per thread, 8 CTAs per SM)",
+            # warp instructions the kernel sent down the ALU pipe (LOP3, shifts, integer adds) per
+            # second of its own CUDA-event time, against what that pipe can take
+            "achieved": (alu_inst / filt_s) if alu_inst else None,
+            "frac": (alu_inst / filt_s / alu_peak) if alu_inst and alu_peak > 0 else None,
+            "alu_warp_instructions": alu_inst, "all_warp_instructions": inst,
+            "issue_slot_frac": (inst / filt_s / issue_peak) if inst else None,
+            "launches": launches_filter,
             "avg_launch_ms": fam["ms_filter"] / max(launches_filter, 1),
             "instruction_count_source": "profiles/r02_filter_inst_counts.json (ncu "
-                                        "smsp__inst_executed.sum on the same states)" if inst else
+                                        "smsp__inst_executed[_pipe_alu].sum on the same states, "
+                                        "scripts/ncu_inst_counts.sh)" if inst else
                                         "missing: run scripts/ncu_inst_counts.sh",
             "traffic": traffic,
             "note": "no contraction in this path and 16.5 KB of operands per search served from "
                     "shared memory: the binding resource is integer-ALU issue, not HBM or tensor "
                     "cores (SURVEY.md 8d); launch durations are CUDA-event times of the kernel "
-                    "running alone",
+                    "running alone; issue_slot_frac = all warp instructions against one per clock "
+                    "per scheduler",
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -715,12 +730,17 @@ def sharded_record(eng, sb, DistributedLutSearch, args, rank, world):
     import torch.distributed as dist
     rec = {}
     target = _rijndael_bit(0)
-    full = np.full(4, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
-    for n in [int(x) for x in args.sharded_gates.split(",") if x]:
+    for spec in [x for x in args.sharded_gates.split(",") if x]:
+        n, half = int(spec.rstrip("h")), spec.endswith("h")
         tabs = _state(n, 4242 + n)
         rs = np.random.RandomState(n)
         o5, oo, om = _orders(rs)
-        eng.load(tabs, target, full, [])
+        # "h": one mux level deep (128 masked positions, the selector bit excluded): the hit list is
+        # not empty, so the list all-gather / merge and the sharded phase 2 carry real data;
+        # otherwise the full mask, the pure sweep
+        fixed = [(7, 1)] if half else []
+        mask, inb = _mux_mask(fixed), [b for b, _ in fixed]
+        eng.load(tabs, target, mask, inb)
 
         def sync():
             torch.cuda.synchronize()
@@ -728,7 +748,10 @@ def sharded_record(eng, sb, DistributedLutSearch, args, rank, world):
                 dist.barrier()
                 torch.cuda.synchronize()
 
-        # unsharded, one GPU (every rank does it: the ranks stay in step and it warms the caches)
+        # unsharded, one GPU (every rank does it: the ranks stay in step); once untimed first --
+        # buffers for a search of this size are allocated on first use
+        eng.search5(o5)
+        eng.search7(oo, om)
         sync()
         t0 = time.perf_counter()
         r5 = eng.search5(o5)
@@ -738,11 +761,15 @@ def sharded_record(eng, sb, DistributedLutSearch, args, rank, world):
         one = (int(r5.key), int(r7.key), int(r7.tuples_feasible))
         lst = eng.filter7_part(0, 1)
         list_hash = hashlib.sha1(lst.tobytes()).hexdigest()
-        entry = {"gates": n, "t_units": math.comb(n, 5) + math.comb(n, 7),
+        entry = {"gates": n, "masked_positions": 128 if fixed else 256,
+                 "t_units": math.comb(n, 5) + int(r7.tuples_swept),
                  "ms_one_gpu": ms_one, "list_len": len(lst)}
         if world > 1:
             drv = DistributedLutSearch(eng, shard_min_tuples5=0, shard_min_tuples7=0, shard_min_list=0)
-            eng.load(tabs, target, full, [])
+            eng.load(tabs, target, mask, inb)
+            drv.search5_sharded(o5)
+            drv.search7_sharded(oo, om)
+            drv.collective_ms = 0.0
             sync()
             c0 = drv.collectives
             t0 = time.perf_counter()
@@ -771,8 +798,8 @@ def sharded_record(eng, sb, DistributedLutSearch, args, rank, world):
         else:
             entry.update({"ms": ms_one, "collectives": 0, "collective_ms": 0.0, "parity": True})
         entry["t_units_per_s"] = entry["t_units"] / (entry["ms"] * 1e-3)
-        rec["n%d" % n] = entry
-    rec["what"] = ("one state per size, full mask, search_5lut + search_7lut of that state sharded over "
+        rec["n" + spec] = entry
+    rec["what"] = ("one state per size, search_5lut + search_7lut of that state sharded over "
                    "the tuple space across all ranks (ms = max over ranks); ms_one_gpu = the same "
                    "search on one GPU in the same run; parity = keys and merged hit list identical")
     return rec
