@@ -571,13 +571,14 @@ def main():
         dev_ms = sum(a.elapsed_time(b) for a, b in ev)
         # results are read from mapped memory while the stream is still draining, so the host's
         # clock and the stream's events bracket slightly different things: report the larger
-        own_ms = max(dev_ms, 1e3 * t_wall) + gather_ms
-        ranks_ms = [own_ms]
+        compute_ms = max(dev_ms, 1e3 * t_wall)
+        own_ms = compute_ms + gather_ms
+        ranks_ms, ranks_compute = [own_ms], [compute_ms]
         if world > 1:
-            t = torch.tensor([own_ms], dtype=torch.float64, device="cuda")
-            allt = torch.empty(world, dtype=torch.float64, device="cuda")
+            t = torch.tensor([own_ms, compute_ms], dtype=torch.float64, device="cuda")
+            allt = torch.empty(2 * world, dtype=torch.float64, device="cuda")
             dist.all_gather_into_tensor(allt, t)
-            ranks_ms = allt.tolist()
+            ranks_ms, ranks_compute = allt.tolist()[0::2], allt.tolist()[1::2]
             u = torch.tensor([acc["T5"], acc["T7"], acc["C"]], dtype=torch.int64, device="cuda")
             dist.all_reduce(u, op=dist.ReduceOp.SUM)
             acc["T5"], acc["T7"], acc["C"] = (int(x) for x in u.tolist())
@@ -585,6 +586,7 @@ def main():
         tr1 = eng.transfer_stats()
         acc["h2d"], acc["d2h"] = tr1[0] - tr0[0], tr1[1] - tr0[1]
         acc["gather_ms"] = gather_ms
+        acc["ranks_compute"] = ranks_compute
         return max(ranks_ms), ranks_ms, acc, clocks
 
     ms_res, ranks_res, acc_res, clocks = timed(resident=True)
@@ -594,17 +596,20 @@ def main():
     # dominant kernel's launch durations for the roofline; not part of `value`
     eng.set_timing(True)
     fam = {"ms5": 0.0, "ms_filter": 0.0, "ms_order": 0.0, "ms_decomp": 0.0}
+    by_depth = {k: [0.0] * 4 for k in ("ms5", "ms_filter", "ms_decomp")}   # mux depth 0..3 of the state
     t7_iso = 0
     for s in range(args.steps):
         states = batches[args.warmup + s]
         stage(states)
         flush.fill_(s & 0xFF)
         torch.cuda.synchronize()
-        for j in jobs_of(states):
+        for i, j in enumerate(jobs_of(states)):
             r = eng.search_batch([j])[0]
             t7_iso += int(r.r7.tuples_swept)
             for k, w in (("ms5", 0), ("ms_filter", 1), ("ms_order", 2), ("ms_decomp", 3)):
                 fam[k] += eng.kernel_ms(w)
+                if k in by_depth:
+                    by_depth[k][i % 4] += eng.kernel_ms(w)
     eng.set_timing(False)
     alu_peak = eng.alu_peak()
     props = torch.cuda.get_device_properties(local_rank)
@@ -677,11 +682,18 @@ def main():
             "c_units_per_s": acc_res["C"] / (ms_res * 1e-3),
             "units_per_step": {"T": (acc_res["T5"] + acc_res["T7"]) // args.steps,
                                "C": acc_res["C"] // args.steps},
-            "per_rank_ms_per_step": {"min": min(ranks_res) / args.steps,
-                                     "mean": sum(ranks_res) / len(ranks_res) / args.steps,
-                                     "max": max(ranks_res) / args.steps,
-                                     "all_gather_wait_ms_total": acc_res["gather_ms"]},
+            # each rank's own searches (before the exchange: ranks hold different states, so their
+            # work differs) and the one key exchange that ends the timed region (NCCL all-gather
+            # plus waiting for the slowest rank)
+            "per_rank_ms_per_step": {"min": min(acc_res["ranks_compute"]) / args.steps,
+                                     "mean": sum(acc_res["ranks_compute"]) / len(ranks_res) / args.steps,
+                                     "max": max(acc_res["ranks_compute"]) / args.steps,
+                                     "with_exchange_max": max(ranks_res) / args.steps,
+                                     "exchange_ms_total_rank0": acc_res["gather_ms"]},
             "kernel_ms_per_step_isolated": {k: v / args.steps for k, v in fam.items()},
+            # the same, split by the states' mux depth 0..3 (256, 128, 64, 32 masked positions)
+            "kernel_ms_per_step_by_mask_depth": {k: [x / args.steps for x in v]
+                                                 for k, v in by_depth.items()},
             "kernel_to_step_ratio": sum(fam.values()) / ms_res if world == 1 else None,
             "e2e": {"value": (acc_e2e["T5"] + acc_e2e["T7"] + acc_e2e["C"]) / (ms_e2e * 1e-3),
                     "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

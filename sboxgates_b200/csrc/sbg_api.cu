@@ -186,6 +186,9 @@ struct sbg_handle {
   int opt_shift = -1;       // SBG_SHIFT: phase-1 shifted single-word windows, 0 never, 1 whenever n <= 63
   int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   int opt_pdl = 1;          // SBG_PDL: programmatic dependent launch between the kernels of a chain
+  int opt_batch_conc = 2;   // SBG_BATCH_CONC: phase-1 prefixes per ticket while several chains share
+                            // the device (sbg_search_batch)
+  bool concurrent = false;  // set while sbg_search_batch enqueues more than one chain
   bool hits_cap_forced = false;
   size_t hits_cap_default = kDefaultHitsCap;
   uint64_t ticket_table_max = kTicketTableMax;
@@ -317,7 +320,10 @@ uint64_t pick_batch(const sbg_handle *h, uint64_t tickets, int n, int P) {
   // position-major kernel, 4-gate prefixes: single prefixes up to n = 72 (measured, scripts/
   // sweep_head.sh / sweep_batch.sh: n = 48 / 64 full mask 1.07 / 7.08 ms against 1.26 / 8.99 ms with
   // the formula below; from n = 80 on the formula's 4 is as good or better)
-  if (P == 4 && n <= kSinglePrefixMaxGates) return 1;
+  // ... when the kernel has the device to itself.  Several chains at once (sbg_search_batch) fill
+  // each other's tails, and what counts is fewer trips to the ticket counter: measured on bench.py's
+  // step (n = 40, 8 states): 2.11 ms with single prefixes, 1.91 ms with pairs, 1.94 ms with fours.
+  if (P == 4 && n <= kSinglePrefixMaxGates) return h->concurrent ? (uint64_t)h->opt_batch_conc : 1;
   const uint64_t total = pm ? h_binom[n - 1][6] : h_binom[n][P + 2];
   const uint64_t avg_pairs = std::max<uint64_t>(1, total / std::max<uint64_t>(1, tickets));
   const uint64_t qmax = P == 6 ? (uint64_t)std::max(1, n - 7) : h_binom[n - P - (P == 4 ? 1 : 0)][2];
@@ -1397,6 +1403,11 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;
   if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));
   if (getenv("SBG_PDL") != nullptr) h->opt_pdl = atoi(getenv("SBG_PDL")) != 0;
+  if (getenv("SBG_BATCH_CONC") != nullptr) {
+    int b = std::max(1, std::min(16, atoi(getenv("SBG_BATCH_CONC"))));
+    while (b & (b - 1)) b &= b - 1;
+    h->opt_batch_conc = b;
+  }
   if (getenv("SBG_TIMING") != nullptr) h->timing = atoi(getenv("SBG_TIMING")) != 0;
   if (getenv("SBG_SEARCH5") != nullptr) {
     h->opt_search5 = strcmp(getenv("SBG_SEARCH5"), "two") == 0 ? 2 : 1;
@@ -1966,6 +1977,7 @@ int sbg_search_batch(sbg_handle *h, int njobs, const sbg_job *jobs, sbg_node_res
   for (int base = 0; base < njobs; base += kLanes) {
     const int wave = std::min(kLanes, njobs - base);
     ChainInfo ci[kLanes];
+    h->concurrent = wave > 1;
     if (wave > 1) SBG_CUDA(h, cudaEventRecord(h->lane[0].ev_done, main_stream));
     for (int k = 0; k < wave; k++) {
       sbg_lane &L = h->lane[k];
@@ -1979,8 +1991,12 @@ int sbg_search_batch(sbg_handle *h, int njobs, const sbg_job *jobs, sbg_node_res
       in.middle = job.middle7;
       in.gate_order = job.gate_order;
       L.list_ready = false;
-      if ((rc = enqueue_chain(h, L, job.flags, in, ci[k])) != SBG_OK) return rc;
+      if ((rc = enqueue_chain(h, L, job.flags, in, ci[k])) != SBG_OK) {
+        h->concurrent = false;
+        return rc;
+      }
     }
+    h->concurrent = false;
     for (int k = 0; k < wave; k++) {
       sbg_lane &L = h->lane[k];
       if ((rc = collect_chain(h, L, &jobs[base + k], ci[k], &results[base + k])) != SBG_OK) return rc;

@@ -52,10 +52,15 @@ struct DevProblem {
 };
 
 struct DevCtl {
+  // The work dispenser gets a cache line of its own: every warp of a sweep takes a ticket with an
+  // atomic on it every few microseconds, and everything else in this block (hit counter, minimum
+  // key, statistics) would otherwise queue up behind those atomics in the same L2 slice.
   unsigned long long ticket;       // next work item
+  unsigned long long pad0[15];
+  unsigned long long hit_count;    // filter7 / two-kernel search5: slots reserved in the hit buffer
+  unsigned long long pad1[15];
   unsigned long long best;         // minimum key found so far by the running stage
   unsigned long long stop_ticket;  // search5: tickets above this cannot improve `best`
-  unsigned long long hit_count;    // filter7 / two-kernel search5: slots reserved in the hit buffer
   unsigned long long swept;        // tuples put through the feasibility test
   unsigned long long feasible;     // search5: feasible tuples met
   unsigned long long ticket2;      // decomp5 / decomp7: next list entry
@@ -676,8 +681,11 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 // of the rows shifted down to the first possible g (31 gates per word, the target bit on top) in
 // its own shared-memory scratch; one word per position then covers every candidate of nearly every
 // prefix and the position loop does half the accumulates.
+#ifndef SBG_FILTER_MIN_CTAS
+#define SBG_FILTER_MIN_CTAS 2
+#endif
 template <int NW, int W, int P, bool FS, bool SH = false>
-__global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__restrict__ prob,
+__global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, uint64_t *__restrict__ hits, uint64_t *__restrict__ aux,
     uint32_t *__restrict__ tcount, uint32_t *__restrict__ gcount, unsigned long long hits_cap,
     unsigned long long tickets_cap, int part, int nparts, unsigned long long list_cap, int batch,
@@ -746,24 +754,52 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
   const uint32_t inmask = prob->inmask;
   const uint64_t total = c_binom[n - (K - P)][P];
   unsigned long long swept_lane = 0;   // T-units this lane put through the test (summed at the end)
-  unsigned long long next_b = 0;
+#ifndef SBG_FETCH_DEPTH
+#define SBG_FETCH_DEPTH 1   // measured (bench.py, n = 40): 1 ticket ahead 1.56 ms, 2 ahead 1.62 ms
+#endif
+  // tickets in flight per warp: with every warp of the machine taking tickets from one counter,
+  // the latency of the atomic under load is of the order of one ticket's work
+  constexpr int kDepth = SBG_FETCH_DEPTH;
+  unsigned long long q_b[kDepth], q_hc[kDepth];
+  unsigned long long next_b = 0, next_hc = 0;
+  // A ticket and the hit count as it stood when the ticket was taken -- two independent requests to
+  // the same cache line, the load first, so neither waits for the other and both have arrived when
+  // they are looked at one ticket later.  The stop rule is evaluated on that pair: a ticket taken
+  // when the cap was already reached is dropped, and (tickets being handed out in order) every hit
+  // counted at that moment came from a lower ticket, so nothing that belongs to the first list_cap
+  // entries is lost.
   auto fetch = [&]() {
     if (lane == 0) {
-      const bool stop = volatile_load(&ctl->hit_count) >= list_cap;
-      next_b = stop ? ~0ull : atomicAdd(&ctl->ticket, 1ull);
+      next_hc = volatile_load(&ctl->hit_count);
+      next_b = atomicAdd(&ctl->ticket, 1ull);
     }
   };
   // In the overflow retry (max_warps > 0) tickets are taken synchronously: a ticket fetched ahead
   // would be worked on even if the cap was reached meanwhile, doubling the hits in flight.
   const bool ahead = max_warps == 0;
   const int n_allowed = n - __popc(inmask & 0xffu);
-  if (ahead) fetch();
+  if (ahead) {
+#pragma unroll
+    for (int i = 0; i < kDepth; i++) {
+      fetch();
+      q_b[i] = next_b;
+      q_hc[i] = next_hc;
+    }
+  }
   for (;;) {
-    if (!ahead) fetch();
-    const unsigned long long b = __shfl_sync(kFull, next_b, 0);
-    if (b == ~0ull) break;
+    if (!ahead) {
+      fetch();
+      q_b[0] = next_b;
+      q_hc[0] = next_hc;
+    }
+    const unsigned long long b = __shfl_sync(kFull, q_b[0], 0);
+    const unsigned long long hc_then = __shfl_sync(kFull, q_hc[0], 0);
     if (b >= tickets_cap) {   // the ticket table is too small for this sweep: the host continues it
-      if (lane == 0) atomicMax(&ctl->overflow, 2u);
+      if (lane == 0 && hc_then < list_cap) atomicMax(&ctl->overflow, 2u);
+      break;
+    }
+    if (hc_then >= list_cap) {   // the list was complete before this ticket was handed out
+      if (lane == 0) tcount[b] = 0;
       break;
     }
     uint32_t tj = 0;          // hits of this ticket so far
@@ -792,7 +828,16 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
       }
       t_end = min(t_first + (uint64_t)batch, total);
     }
-    if (ahead) fetch();
+    if (ahead) {   // the queue moves up, a new ticket is requested for its end
+#pragma unroll
+      for (int i = 0; i + 1 < kDepth; i++) {
+        q_b[i] = q_b[i + 1];
+        q_hc[i] = q_hc[i + 1];
+      }
+      fetch();
+      q_b[kDepth - 1] = next_b;
+      q_hc[kDepth - 1] = next_hc;
+    }
     if (valid) {
     int pre[P];
     uint64_t unused_rank;
@@ -872,12 +917,9 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
         if (lane_ok) swept_lane += (unsigned long long)(n - 1 - gf);   // T-units: every g > f
         if (P == 4 && ge < 8 && ((inmask >> ge) & 1u)) lane_ok = false;
         if (gf < 8 && ((inmask >> gf) & 1u)) lane_ok = false;
-        uint32_t te[NW], tf[NW];
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-          te[w] = s_tabs[w * npad + ge];
-          tf[w] = s_tabs[w * npad + gf];
-        }
+        // the lane's e / f tables are read from shared memory word by word where they are used
+        // (once per cell and word) instead of living in 2 x NW registers across the whole chunk
+        const uint32_t *tab_e = s_tabs + ge, *tab_f = s_tabs + gf;
         // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
         // (SH: windows of 31 gates starting AT the smallest possible g, wb counts them)
         const int first_g = last + (K - P);
@@ -936,6 +978,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
 #pragma unroll
             for (int w = 0; w < NW; w++) {
               uint32_t bits = cells[cj * NW + w];
+              const uint32_t tf_w = tab_f[w * npad];
+              const uint32_t te_w = P == 4 ? tab_e[w * npad] : 0u;
               // shared-window address of row w*32+31 of this window (aligned two-word windows)
               const uint32_t row_top = xr_base + (uint32_t)((w * 32 + 31) * ngw + wb) * 4u;
               while (bits != 0) {                     // warp-uniform loop over the cell's positions
@@ -948,8 +992,8 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
                 // eb / fb = bit j of the lane's e / f table spread over a whole word (shift it to
                 // the sign position, arithmetic shift back): all-ones / zero masks without a
                 // predicate, so that every masked accumulate below is ONE three-input LOP3.
-                const uint32_t fb = (uint32_t)((int32_t)(tf[w] << c) >> 31);
-                const uint32_t eb = P == 4 ? (uint32_t)((int32_t)(te[w] << c) >> 31) : 0u;
+                const uint32_t fb = (uint32_t)((int32_t)(tf_w << c) >> 31);
+                const uint32_t eb = P == 4 ? (uint32_t)((int32_t)(te_w << c) >> 31) : 0u;
                 uint32_t x[W];
                 if (W == 2) {
                   const uint2 xx = lds_v2(row_top + neg_row_bytes * (uint32_t)c);
@@ -1013,6 +1057,7 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
         // emit the chunk: lane-major (= (e,f) order), then g ascending
         int cnt = 0;
         for (int i = 0; i < nvw; i++) cnt += __popc(vs[i * 32 + lane]);
+        if (!__any_sync(kFull, cnt != 0)) continue;   // the common case: nothing survived
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1020,7 +1065,6 @@ __global__ void __launch_bounds__(kThreads) k_filter7_pm(const DevProblem *__res
           if (lane >= d) incl += up;
         }
         const int warp_total = __shfl_sync(kFull, incl, 31);
-        if (warp_total == 0) continue;
         unsigned long long base_slot = 0;
         if (lane == 0) base_slot = atomicAdd(&ctl->hit_count, (unsigned long long)warp_total);
         base_slot = __shfl_sync(kFull, base_slot, 0) + (unsigned long long)(incl - cnt);
@@ -1332,6 +1376,14 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
   }
   __shared__ uint8_t posm[256];
   __shared__ uint8_t s_min[kMinpos3 + 3];
+  __shared__ uint32_t s_info[kMinpos3];
+  __shared__ int s_level[10];
+  // the visiting order of minpos3 (26 KB): all loads in flight at once, instead of one dependent
+  // round trip to L2 per level of the sweep below
+  if (a.flags & kBeginSearch7) {
+    for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_info[i] = tab->m3_info[i];
+    if (threadIdx.x < 10) s_level[threadIdx.x] = tab->m3_level[threadIdx.x];
+  }
   if (threadIdx.x == 0) {
     if (a.flags & kBeginKeepCtl) {   // phase 2 on an installed list: keep the list, restart the rest
       ctl->best = ~0ull;
@@ -1342,14 +1394,20 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
       ctl->skip7 = 0;
       ctl->seq = a.seq;
     } else {
-      DevCtl c;
-      memset(&c, 0, sizeof(c));
-      c.best = ~0ull;
-      c.stop_ticket = ~0ull;
-      c.seq = a.seq;
-      c.skip5 = (a.flags & kBeginSearch5) ? 0u : 1u;
-      c.skip7 = (a.flags & kBeginSearch7) ? 0u : 1u;
-      *ctl = c;
+      ctl->ticket = 0;
+      ctl->hit_count = 0;
+      ctl->best = ~0ull;
+      ctl->stop_ticket = ~0ull;
+      ctl->swept = 0;
+      ctl->feasible = 0;
+      ctl->ticket2 = 0;
+      ctl->seq = a.seq;
+      ctl->overflow = 0;
+      ctl->list_count = 0;
+      ctl->ctas_done = 0;
+      ctl->stage_found = 0;
+      ctl->skip5 = (a.flags & kBeginSearch5) ? 0u : 1u;
+      ctl->skip7 = (a.flags & kBeginSearch7) ? 0u : 1u;
     }
   }
   if (!(a.flags & kBeginKeepCtl)) {
@@ -1370,9 +1428,9 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
   __syncthreads();
   int lo = 0;
   for (int level = 0; level <= 8; level++) {
-    const int hi = tab->m3_level[level + 1];
+    const int hi = s_level[level + 1];
     for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-      const uint32_t info = tab->m3_info[i];
+      const uint32_t info = s_info[i];
       const uint32_t e = info & 0x1fffu;
       if (level == 0) {
         s_min[e] = posm[info >> 16];

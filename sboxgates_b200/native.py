@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsboxgates_b200.so")
+# SBG_LIB: another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("SBG_LIB") or os.path.join(_HERE, "libsboxgates_b200.so")
 
 SBG_OK = 0
 SBG_LIST_CAP = 100000
