@@ -96,6 +96,10 @@ float sbg_last_kernel_ms(const sbg_handle *h, int which);
    memory and copies), out[2..4] = state changes that took a bulk copy / travelled as kernel
    arguments / were no change at all. */
 int sbg_transfer_stats(const sbg_handle *h, uint64_t *out /*5*/);
+/* Host seconds sbg_search_node() has spent so far: out[0] = enqueueing the chains (launch calls),
+   out[1] = waiting for and decoding their results; out[2..4] = the waiting alone, per stage
+   (3-LUT scan, search_5lut, search_7lut; all calls of the handle). */
+int sbg_host_seconds(const sbg_handle *h, double *out /*5*/);
 /* Measures the device's LOP3 issue rate (warp instructions per second, whole chip): the ceiling
    the search kernels are bound by. */
 int sbg_alu_peak(sbg_handle *h, double *warp_instr_per_s);
@@ -145,7 +149,8 @@ typedef struct {
   int32_t found_stage;         /* 0 nothing, else 3 / 5 / 7 */
   uint16_t gates3[3];          /* stage 3: LUT inputs in gate_order order (gi, gk, gm) */
   uint8_t func3, seen3;        /* solved function bits / cells seen under the mask (fill as below) */
-  uint64_t key3;               /* rank of the position triple in gate_order, or SBG_KEY_NONE */
+  uint64_t key3;               /* the position triple in gate_order, i << 18 | k << 9 | m, or
+                                  SBG_KEY_NONE */
   sbg_result r5;               /* as sbg_search5 (found = 0 if the stage did not run) */
   sbg_result r7;               /* as sbg_search7 */
 } sbg_node_result;

@@ -158,6 +158,15 @@ static void shim_exit(void) {
         (unsigned long long)sbg_launch_count(g_handle), (unsigned long long)tr[2],
         (unsigned long long)tr[3], (unsigned long long)tr[4], (unsigned long long)tr[0],
         (unsigned long long)tr[1]);
+    double hs[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    sbg_host_seconds(g_handle, hs);
+    if (g_calls[2] != 0) {
+      fprintf(stderr, "[sbg] node calls: %.3f s enqueueing chains, %.3f s waiting for results, "
+          "%.3f s around them (flattening the state, shuffles, add_lut)\n", hs[0], hs[1],
+          g_seconds[2] - g_init_seconds - hs[0] - hs[1]);
+    }
+    fprintf(stderr, "[sbg] waiting by stage: 3-LUT scan %.3f s, search_5lut %.3f s, search_7lut "
+        "%.3f s\n", hs[2], hs[3], hs[4]);
     if (getenv("SBG_TIMING") != NULL) {
       fprintf(stderr, "[sbg] kernel time: search5 %.3f s, filter7 %.3f s, ordering %.3f s, "
           "decomp7 %.3f s\n", 1e-3 * g_kernel_ms[0], 1e-3 * g_kernel_ms[1], 1e-3 * g_kernel_ms[2],

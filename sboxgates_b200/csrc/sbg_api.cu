@@ -186,6 +186,8 @@ struct sbg_handle {
   int opt_shift = -1;       // SBG_SHIFT: phase-1 shifted single-word windows, 0 never, 1 whenever n <= 63
   int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   int opt_pdl = 1;          // SBG_PDL: programmatic dependent launch between the kernels of a chain
+  int opt_speculate = 1;    // SBG_SPECULATE: see enqueue_chain
+  int opt_decomp_filter = 1;  // SBG_DECOMP_FILTER: lane-parallel stage-1 filter of phase 2 (0 = ballot form only)
   int opt_batch_conc = 2;   // SBG_BATCH_CONC: phase-1 prefixes per ticket while several chains share
                             // the device (sbg_search_batch)
   bool concurrent = false;  // set while sbg_search_batch enqueues more than one chain
@@ -197,6 +199,8 @@ struct sbg_handle {
   uint64_t uploads_full = 0, uploads_incremental = 0, uploads_skipped = 0;
   uint64_t h2d_bytes = 0, d2h_bytes = 0;   // problem data shipped / results read, over the handle's life
   float last_ms[4] = {0, 0, 0, 0};         // kernel families of the last call (timing mode)
+  double host_s[2] = {0, 0};               // host seconds: enqueueing chains, waiting + decoding
+  double wait_s[3] = {0, 0, 0};            // of the waiting: for the 3-LUT scan, search_5lut, search_7lut
   char err[512] = {0};
 };
 
@@ -231,12 +235,6 @@ template <int NW>
 size_t decomp_smem(int n) {
   const int npad = (n + 3) & ~3;
   return sizeof(uint32_t) * (size_t)(NW * npad);
-}
-
-template <int NW>
-size_t scan3_smem(int n) {
-  const int npad = (n + 3) & ~3;
-  return sizeof(uint32_t) * (size_t)(NW * npad) + sizeof(uint16_t) * (size_t)((n + 1) & ~1);
 }
 
 // Kernels whose dynamic shared memory can exceed the 48 KB default opt in once per size class.
@@ -467,12 +465,19 @@ void record_done(sbg_handle *h, sbg_lane &L) {
 
 // ---- waiting for a stage ---------------------------------------------------------------------
 
+double wall_now() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 // Spins on the lane's mapped result block until the device has stored this call's sequence number
 // for `stage`.  No CUDA call on the fast path; every ~2 ms of waiting the stream is queried so that
 // a failed launch turns into an error instead of a hang.
 int wait_stage(sbg_handle *h, sbg_lane &L, int stage) {
   volatile unsigned long long *flag = &L.h_out->seq[stage];
   uint64_t spins = 0;
+  const double t_wait = wall_now();
   while (*flag != L.seq) {
     __builtin_ia32_pause();
     if ((++spins & 0x3ffff) == 0) {
@@ -486,6 +491,7 @@ int wait_stage(sbg_handle *h, sbg_lane &L, int stage) {
     }
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  h->wait_s[stage] += wall_now() - t_wait;
   return SBG_OK;
 }
 
@@ -515,29 +521,6 @@ struct CallInputs {
 };
 
 int enqueue_begin(sbg_handle *h, sbg_lane &L, uint32_t flags, const CallInputs &in, uint32_t gcount_n);
-
-int enqueue_scan3(sbg_handle *h, sbg_lane &L) {
-  const sbg_handle::HostProblem &hp = h->slots[L.slot];
-  const int n = hp.n;
-  const uint64_t triples = h_binom[n][3];
-  cudaError_t e = cudaSuccess;
-#define SBG_LAUNCH_SCAN3(NWV)                                                                  \
-  {                                                                                            \
-    const size_t smem = scan3_smem<NWV>(n);                                                    \
-    const int grid = grid_for(h, k_scan3<NWV>, smem, (triples + 31) / 32);                     \
-    e = launch(h, k_scan3<NWV>, grid, kThreads, smem, L.stream, true, h->d_slots + L.slot,     \
-        L.d_ctl, L.d_out, L.d_order3);                                                         \
-  }
-  switch (hp.nw) {
-    case 1: SBG_LAUNCH_SCAN3(1) break;
-    case 2: SBG_LAUNCH_SCAN3(2) break;
-    case 4: SBG_LAUNCH_SCAN3(4) break;
-    default: SBG_LAUNCH_SCAN3(8) break;
-  }
-#undef SBG_LAUNCH_SCAN3
-  if (e != cudaSuccess) return fail(h, SBG_ERR_CUDA, "k_scan3: %s", cudaGetErrorString(e));
-  return SBG_OK;
-}
 
 // search_5lut.  Small searches (the bulk of a real run) use two kernels -- a sweep that only
 // records feasible tuples, then one warp per recorded tuple -- so that the decomposition of several
@@ -775,7 +758,8 @@ int enqueue_decomp7(sbg_handle *h, sbg_lane &L, int part, int nparts, uint64_t i
     const size_t smem = decomp_smem<NWV>(n);                                                   \
     const int grid = grid_for(h, k_decomp7<NWV>, smem, items_hint);                            \
     e = launch(h, k_decomp7<NWV>, grid, kThreads, smem, L.stream, !h->timing,                  \
-        h->d_slots + L.slot, L.d_ctl, L.d_out, L.d_par7, L.d_sorted, part, nparts, h->d_tab);  \
+        h->d_slots + L.slot, L.d_ctl, L.d_out, L.d_par7, L.d_sorted, part, nparts, h->d_tab,   \
+        h->opt_decomp_filter);                                                                 \
   }
   switch (hp.nw) {
     case 1: SBG_LAUNCH_DECOMP(1) break;
@@ -926,8 +910,15 @@ int apply_pending(sbg_handle *h, int slot, cudaStream_t stream, BeginArgs &a, bo
 
 int prep_ctas(const sbg_handle::HostProblem &hp, const BeginArgs &a) {
   if (!(a.flags & kBeginProblem)) return 0;
+  // warp items (one 32-bit word each): compressed tables, position-major rows; 32 warps per block,
+  // a few items per warp
   const int items = std::max((hp.n - a.c_first) * 8, (a.flags & kBeginRows) ? hp.m * 16 : 0);
-  return std::max(1, std::min(8, (items + 1023) / 1024));
+  return std::max(1, std::min(64, (items + 127) / 128));
+}
+
+int scan_ctas(const sbg_handle *h, int n) {
+  const int pairs = n * (n - 1) / 2;
+  return std::max(1, std::min(4 * h->sm_count, (pairs + 63) / 64));
 }
 
 int stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n, const uint64_t *target,
@@ -1022,15 +1013,16 @@ int enqueue_begin(sbg_handle *h, sbg_lane &L, uint32_t flags, const CallInputs &
       memset(a.pos_middle, 0, 256);
     }
   }
-  if (flags & kBeginScan3) {
-    a.flags |= kBeginOrder3;
-    memcpy(a.order3, in.gate_order, sizeof(uint16_t) * (size_t)hp.n);
-  }
+  if (flags & kBeginScan3) memcpy(a.order3, in.gate_order, sizeof(uint16_t) * (size_t)hp.n);
   int rc = apply_pending(h, L.slot, L.stream, a, (flags & kBeginRows) != 0);
   if (rc != SBG_OK) return rc;
-  const int ctas = prep_ctas(hp, a);
-  const cudaError_t e = launch(h, k_begin, 1 + ctas, 1024, 0, L.stream, false,
-      h->d_slots + L.slot, L.d_ctl, L.d_par7, L.d_pos5, L.d_order3, L.d_gcount, h->d_tab, a);
+  const int prep = prep_ctas(hp, a);
+  const int scan = (flags & kBeginScan3) ? scan_ctas(h, hp.n) : 0;
+  // block 0 keeps the minpos3 visiting order, the scan blocks the uncompressed tables, in dynamic
+  // shared memory
+  const size_t smem = std::max<size_t>(sizeof(uint32_t) * kMinpos3, (size_t)hp.n * 32);
+  const cudaError_t e = launch(h, k_begin, 1 + prep + scan, 1024, smem, L.stream, false,
+      h->d_slots + L.slot, L.d_ctl, L.d_out, L.d_par7, L.d_pos5, L.d_gcount, h->d_tab, prep, a);
   if (e != cudaSuccess) return fail(h, SBG_ERR_CUDA, "k_begin: %s", cudaGetErrorString(e));
   return SBG_OK;
 }
@@ -1055,11 +1047,32 @@ int enqueue_chain(sbg_handle *h, sbg_lane &L, int what, const CallInputs &in, Ch
   }
   if (flags & kBeginSearch5) ci.two5 = search5_two_kernels(h, hp.n);
   if ((rc = enqueue_begin(h, L, flags, in, gcount_n)) != SBG_OK) return rc;
-  if ((flags & kBeginScan3) && (rc = enqueue_scan3(h, L)) != SBG_OK) return rc;
-  if ((flags & kBeginSearch5) && (rc = enqueue_search5(h, L, 0, 1, ci.two5)) != SBG_OK) return rc;
-  if (flags & kBeginSearch7) {
+  // How far ahead of the results to launch (SBG_SPECULATE; single calls -- a batch always launches
+  // whole chains, its lanes keep the device busy).  Half of a graph build's nodes end at the 3-LUT
+  // scan, which runs inside that first kernel, and a third at search_5lut: the kernels of the later
+  // stages would return at once, but launching and draining hundreds of empty blocks still occupies
+  // the stream for 15-20 us, which the NEXT node's chain then waits behind.  So by default the host
+  // looks at the scan's result before it launches search_5lut + search_7lut (one idle launch latency
+  // for the nodes that go on, against the drain for the ones that do not); 0 = also wait for
+  // search_5lut before launching search_7lut; 2 = launch everything at once.
+  const volatile HostOut *o = L.h_out;
+  const int policy = h->concurrent ? 2 : h->opt_speculate;
+  if ((flags & kBeginScan3) && policy < 2 && (flags & (kBeginSearch5 | kBeginSearch7))) {
+    if ((rc = wait_stage(h, L, 0)) != SBG_OK) return rc;
+  }
+  auto over = [&]() {
+    return (flags & kBeginScan3) && o->seq[0] == L.seq && o->key[0] != SBG_KEY_NONE;
+  };
+  if ((flags & kBeginSearch5) && !over()
+      && (rc = enqueue_search5(h, L, 0, 1, ci.two5)) != SBG_OK) return rc;
+  bool stop = over();
+  if (!stop && policy == 0 && (flags & kBeginSearch5) && (flags & kBeginSearch7)) {
+    if ((rc = wait_stage(h, L, 1)) != SBG_OK) return rc;
+    stop = o->key[1] != SBG_KEY_NONE || o->overflow[1] != 0;
+  }
+  if ((flags & kBeginSearch7) && !stop) {
     if ((rc = enqueue_filter7(h, L, ci.fp, 0, 1)) != SBG_OK) return rc;
-    if ((rc = enqueue_decomp7(h, L, 0, 1, SBG_LIST_CAP)) != SBG_OK) return rc;
+    if (!over() && (rc = enqueue_decomp7(h, L, 0, 1, SBG_LIST_CAP)) != SBG_OK) return rc;
   }
   record_done(h, L);
   return SBG_OK;
@@ -1084,8 +1097,7 @@ int check_job(sbg_handle *h, const sbg_job *job) {
 
 void decode3(const sbg_handle::HostProblem &hp, uint64_t key, const uint16_t *gate_order,
     sbg_node_result *res) {
-  uint16_t pos[3];
-  unrank_combination(key, hp.n, 3, pos);
+  const int pos[3] = {(int)((key >> 18) & 0x1ff), (int)((key >> 9) & 0x1ff), (int)(key & 0x1ff)};
   for (int i = 0; i < 3; i++) res->gates3[i] = gate_order[pos[i]];
   res->key3 = key;
   // check_n_lut_possible(3, ...) held, so get_lut_function cannot fail (lut.c:510-516)
@@ -1403,6 +1415,10 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;
   if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));
   if (getenv("SBG_PDL") != nullptr) h->opt_pdl = atoi(getenv("SBG_PDL")) != 0;
+  if (getenv("SBG_DECOMP_FILTER") != nullptr) {   // 0 off, 1 by list length, 2..32 forced block size
+    h->opt_decomp_filter = std::max(0, std::min(32, atoi(getenv("SBG_DECOMP_FILTER"))));
+  }
+  if (getenv("SBG_SPECULATE") != nullptr) h->opt_speculate = std::max(0, std::min(2, atoi(getenv("SBG_SPECULATE"))));
   if (getenv("SBG_BATCH_CONC") != nullptr) {
     int b = std::max(1, std::min(16, atoi(getenv("SBG_BATCH_CONC"))));
     while (b & (b - 1)) b &= b - 1;
@@ -1427,7 +1443,12 @@ int sbg_create(sbg_handle **out, int device) {
     for (int k = 0; k < 8; k++) SBG_CUDA(h, cudaEventCreate(&L.ev[k]));
     SBG_CUDA(h, cudaEventCreateWithFlags(&L.ev_done, cudaEventDisableTiming));
     SBG_CUDA(h, cudaMalloc(&L.d_ctl, sizeof(DevCtl)));
-    SBG_CUDA(h, cudaMemset(L.d_ctl, 0, sizeof(DevCtl)));
+    {
+      DevCtl init;
+      memset(&init, 0, sizeof(init));
+      init.best3 = ~0ull;   // the 3-LUT scan expects (and leaves) ~0 here
+      SBG_CUDA(h, cudaMemcpy(L.d_ctl, &init, sizeof(init), cudaMemcpyHostToDevice));
+    }
     SBG_CUDA(h, cudaMalloc(&L.d_par7, sizeof(DevParams7)));
     SBG_CUDA(h, cudaMalloc(&L.d_pos5, 256));
     SBG_CUDA(h, cudaMalloc(&L.d_order3, 512 * sizeof(uint16_t)));
@@ -1600,6 +1621,16 @@ int sbg_set_timing(sbg_handle *h, int on) {
 }
 
 uint64_t sbg_launch_count(const sbg_handle *h) { return h != nullptr ? h->launches : 0; }
+
+int sbg_host_seconds(const sbg_handle *h, double *out) {
+  if (h == nullptr || out == nullptr) return SBG_ERR_ARG;
+  out[0] = h->host_s[0];
+  out[1] = h->host_s[1];
+  out[2] = h->wait_s[0];
+  out[3] = h->wait_s[1];
+  out[4] = h->wait_s[2];
+  return SBG_OK;
+}
 
 int sbg_transfer_stats(const sbg_handle *h, uint64_t *out) {
   if (h == nullptr || out == nullptr) return SBG_ERR_ARG;
@@ -1936,6 +1967,7 @@ int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
 int sbg_search_node(sbg_handle *h, const sbg_job *job, sbg_node_result *res) {
   if (h == nullptr || job == nullptr || res == nullptr) return SBG_ERR_ARG;
   int rc;
+  const double t0 = wall_now();
   if ((rc = check_job(h, job)) != SBG_OK) return rc;
   SBG_CUDA(h, cudaSetDevice(h->device));
   sbg_lane &L = h->lane[0];
@@ -1950,7 +1982,10 @@ int sbg_search_node(sbg_handle *h, const sbg_job *job, sbg_node_result *res) {
   ChainInfo ci;
   L.list_ready = false;
   if ((rc = enqueue_chain(h, L, job->flags, in, ci)) != SBG_OK) return rc;
+  const double t1 = wall_now();
   if ((rc = collect_chain(h, L, job, ci, res)) != SBG_OK) return rc;
+  h->host_s[0] += t1 - t0;
+  h->host_s[1] += wall_now() - t1;
   if (h->timing) {
     // timing events sit behind the whole chain: wait for it (the timed mode is for measurements)
     SBG_CUDA(h, cudaStreamSynchronize(L.stream));

@@ -17,6 +17,9 @@
 // per-launch DRAM traffic is the 16.5 KB problem block plus the hit list.
 #pragma once
 
+#ifdef SBG_COUNT_STAGE1
+#include <cstdio>
+#endif
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,9 +71,16 @@ struct DevCtl {
   unsigned int overflow;           // 1: hit buffer too small, 2: ticket table too small
   unsigned int list_count;         // written by k_offsets: entries of the ordered list (<= cap)
   unsigned int ctas_done;          // last-CTA detection of the stage-closing kernels
-  unsigned int stage_found;        // 0, or 3 / 5 once that stage matched (0xff: a stage was left
-                                   // incomplete): later stages of the chain return at once
   unsigned int skip5, skip7;       // stages not asked for (node calls)
+  // seq << 8 | code once a stage of chain `seq` matched (code 3 / 5 / 7) or was left incomplete
+  // (0xff): the later stages of that chain return at once.  Tagged with the sequence number so that
+  // nobody has to reset it -- the 3-LUT scan runs inside the chain's first kernel, next to the
+  // block that installs the other control words.
+  unsigned long long found;
+  // the 3-LUT scan's own words; its closing block leaves them as it found them (~0 and 0)
+  unsigned long long best3;
+  unsigned int scan_done;
+  unsigned int pad2;
 };
 
 // What the device tells the host, in MAPPED PINNED host memory, one block per lane: the last CTA of
@@ -217,6 +227,12 @@ __device__ __forceinline__ void let_successor_start() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Has an earlier stage of this chain matched (or been left incomplete)?
+__device__ __forceinline__ bool chain_is_over(const DevCtl *ctl) {
+  const unsigned long long f = volatile_load(&ctl->found);
+  return (f >> 8) == volatile_load(&ctl->seq) && (f & 0xffull) != 0;
+}
+
 // End of a stage-closing kernel.  Every CTA calls it (no early returns in those kernels); exactly one
 // -- the last to arrive -- gets `true`, with every other CTA's global writes visible to it.
 __device__ __forceinline__ bool last_cta_of_grid(DevCtl *ctl) {
@@ -250,8 +266,9 @@ __device__ __forceinline__ void close_stage(DevCtl *ctl, HostOut *out, int stage
     out->tuple = tuple;
     out->tuple_prev = tuple_prev;
   }
-  if (key != ~0ull) ctl->stage_found = 3 + 2 * stage;      // later stages of the chain return at once
-  else if (overflow != 0) ctl->stage_found = 0xffu;        // incomplete stage: the host redoes it
+  const unsigned long long tag = ctl->seq << 8;
+  if (key != ~0ull) ctl->found = tag | (unsigned long long)(3 + 2 * stage);   // later stages return at once
+  else if (overflow != 0) ctl->found = tag | 0xffull;      // incomplete stage: the host redoes it
   ctl->ticket = 0;
   ctl->ticket2 = 0;
   ctl->hit_count = 0;
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   uint32_t *cells = smem + NW * npad + warp * (NC * 2 * NW);  // per mixed cell: C1[NW], C0[NW]
 
   stage_tables(s_tabs, prob, NW, npad);
-  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip5) != 0;
+  const bool skip = chain_is_over(ctl) || volatile_load32(&ctl->skip5) != 0;
   if (!skip) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
   __syncthreads();
@@ -621,7 +638,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
   uint32_t *s_tabs = smem;
   const int lane = threadIdx.x & 31;
   stage_tables(s_tabs, prob, NW, npad);
-  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip5) != 0;
+  const bool skip = chain_is_over(ctl) || volatile_load32(&ctl->skip5) != 0;
   const unsigned long long count = ctl->hit_count;
   if (!skip && ctl->overflow == 0 && (unsigned long long)blockIdx.x * kWarpsPerCta < count) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
@@ -733,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
   // (max_warps is never negative; the arithmetic only hides the constant from constant folding)
   const uint32_t low31 = 0x7fffffffu ^ ((uint32_t)max_warps >> 31);
 
-  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  if (chain_is_over(ctl) || volatile_load32(&ctl->skip7) != 0) return;
   // position-major rows: 8-byte cp.async chunks, one row per warp at a time (no division); they
   // complete together with the gate-major tables (stage_tables commits and waits for both)
   for (int p = warp; p < m; p += kWarpsPerCta) {
@@ -1127,7 +1144,7 @@ __global__ void __launch_bounds__(256) k_offsets(DevCtl *__restrict__ ctl,
   __shared__ unsigned long long s_part[8];
   __shared__ uint32_t s_scan[8];
   wait_for_predecessor();
-  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  if (chain_is_over(ctl) || volatile_load32(&ctl->skip7) != 0) return;
   const unsigned long long handed = min(volatile_load(&ctl->ticket), tickets_cap);
   const unsigned long long first = (unsigned long long)blockIdx.x * kTicketGroup;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1176,7 +1193,7 @@ __global__ void __launch_bounds__(256) k_scatter(DevCtl *__restrict__ ctl,
     const uint32_t *__restrict__ toffset, uint64_t *__restrict__ sorted,
     unsigned long long hits_cap, unsigned int list_cap) {
   wait_for_predecessor();
-  if (volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0) return;
+  if (chain_is_over(ctl) || volatile_load32(&ctl->skip7) != 0) return;
   if (volatile_load32(&ctl->overflow) == 1u) return;   // incomplete hit buffer: the host retries
   const unsigned long long count = min(volatile_load(&ctl->hit_count), hits_cap);
   for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < count;
@@ -1255,14 +1272,20 @@ struct BeginArgs {
 constexpr uint32_t kBeginScan3 = 1, kBeginSearch5 = 2, kBeginSearch7 = 4, kBeginRows = 8,
     kBeginKeepCtl = 16, kBeginOrder3 = 32, kBeginProblem = 64;
 
-// Derives the search's working set from the resident uncompressed tables (CTAs 1.. of k_begin, or
-// all CTAs of k_prepare_problem): tables compressed to the masked positions (word-major tabs, T, M;
+// Derives the search's working set from the resident uncompressed tables (CTAs of k_begin, or all
+// CTAs of k_prepare_problem): tables compressed to the masked positions (word-major tabs, T, M;
 // every test of the path is "under the mask", lut.c:38-42,86), the header, and -- when asked -- the
 // position-major rows xr: bit g of row p = gate g at masked position p, the row complemented where
 // the target is 0; with n <= 31 / n <= 63 the top bit of word 0 / 1 is no gate and carries the
-// position's target bit.  No CTA depends on another's output: a thread reads a gate from the
-// arguments if it travels there, else from DevProblem::full (which this launch writes for the
-// travelling gates only).
+// position's target bit.  One warp builds one 32-bit word at a time (lane = bit, one ballot).  No CTA
+// depends on another's output: a gate is read from the arguments if it travels there, else from
+// DevProblem::full (which this launch writes for the travelling gates only).
+__device__ __forceinline__ uint32_t arg_or_resident(const DevProblem *prob, const BeginArgs &a, int g,
+    int w) {
+  const int k = g - a.a_first;
+  return (k >= 0 && k < a.a_count) ? a.newg[k][w] : prob->full[g][w];
+}
+
 __device__ __forceinline__ void prepare_problem(DevProblem *__restrict__ prob, const BeginArgs &a,
     int cta, int nctas) {
   __shared__ uint8_t s_posn[256];   // i-th masked position
@@ -1286,10 +1309,10 @@ __device__ __forceinline__ void prepare_problem(DevProblem *__restrict__ prob, c
   __syncthreads();
   const int n = a.n;
   const int nw = m <= 32 ? 1 : m <= 64 ? 2 : m <= 128 ? 4 : 8;
-  auto gate_word = [&](int g, int w) -> uint32_t {
-    const int k = g - a.a_first;
-    return (k >= 0 && k < a.a_count) ? a.newg[k][w] : prob->full[g][w];
-  };
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int wid = cta * warps + (threadIdx.x >> 5);
+  const int nwarps = nctas * warps;
   if (cta == 0 && threadIdx.x < 8) {
     const int w = threadIdx.x;
     uint32_t t = 0, mm = 0;
@@ -1312,45 +1335,40 @@ __device__ __forceinline__ void prepare_problem(DevProblem *__restrict__ prob, c
       prob->m = m;
     }
   }
-  const int tid = cta * blockDim.x + threadIdx.x;
-  const int nthreads = nctas * blockDim.x;
-  // compressed tables: one thread per (gate, word); all 8 words are written (zero above nw) so that
-  // no stale bits survive a change of mask
-  for (int it = tid; it < (n - a.c_first) * 8; it += nthreads) {
+  // compressed tables: warp item = (gate, word); all 8 words are written (zero above nw) so that no
+  // stale bits survive a change of mask
+  for (int it = wid; it < (n - a.c_first) * 8; it += nwarps) {
     const int g = a.c_first + (it >> 3), w = it & 7;
-    uint32_t out = 0;
-    if (w < nw) {
-      uint32_t src[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) src[k] = gate_word(g, k);
-      for (int i = 0; i < 32; i++) {
-        const int ci = w * 32 + i;
-        if (ci >= m) break;
-        const int p = s_posn[ci];
-        uint32_t word = src[0];
-#pragma unroll
-        for (int k = 1; k < 8; k++) word = (p >> 5) == k ? src[k] : word;
-        out |= ((word >> (p & 31)) & 1u) << i;
-      }
+    const int ci = w * 32 + lane;
+    uint32_t bit = 0;
+    if (w < nw && ci < m) {
+      const int p = s_posn[ci];
+      bit = (arg_or_resident(prob, a, g, p >> 5) >> (p & 31)) & 1u;
     }
-    prob->tabs[w][g] = out;
+    const uint32_t out = __ballot_sync(kFull, bit != 0);
+    if (lane == 0) prob->tabs[w][g] = out;
     // the travelling gates become resident
-    if (g >= a.a_first && g < a.a_first + a.a_count) prob->full[g][w] = a.newg[g - a.a_first][w];
+    if (lane == 1 && g >= a.a_first && g < a.a_first + a.a_count) {
+      prob->full[g][w] = a.newg[g - a.a_first][w];
+    }
   }
   if (a.flags & kBeginRows) {
     const int spare = n <= 31 ? 31 : (n <= 63 ? 63 : -1);
-    for (int it = tid; it < m * 16; it += nthreads) {
+    const int ngw = (n + 31) >> 5;             // gate words that hold gates
+    for (int it = wid; it < m * 16; it += nwarps) {
       const int p = it >> 4, gw = it & 15;
-      const int pp = s_posn[p];
       uint32_t word = 0;
-      const int g_end = min(n, gw * 32 + 32);
-      for (int g = gw * 32; g < g_end; g++) {
-        word |= ((gate_word(g, pp >> 5) >> (pp & 31)) & 1u) << (g & 31);
-      }
+      const int pp = s_posn[p];
       const bool t1 = ((s_target[pp >> 5] >> (pp & 31)) & 1u) != 0;
+      if (gw < ngw) {
+        const int g = gw * 32 + lane;
+        uint32_t bit = 0;
+        if (g < n) bit = (arg_or_resident(prob, a, g, pp >> 5) >> (pp & 31)) & 1u;
+        word = __ballot_sync(kFull, bit != 0);
+      }
       if (!t1) word = ~word;
       if (spare >= 0 && gw == (spare >> 5)) word = t1 ? (word | 0x80000000u) : (word & 0x7fffffffu);
-      prob->xr[p][gw] = word;
+      if (lane == 0) prob->xr[p][gw] = word;
     }
   }
 }
@@ -1361,22 +1379,114 @@ __global__ void __launch_bounds__(1024) k_prepare_problem(DevProblem *__restrict
   prepare_problem(prob, a, blockIdx.x, gridDim.x);
 }
 
-// CTA 0: control words, position tables, ticket-group counters, and minpos3 (see DevParams7) by
-// dynamic programming over the number of unconstrained bits: an entry with a free bit j is the
-// minimum of the two entries that force bit j (entries are visited level by level through
-// DevTables::m3_info, which lists them by number of free bits).
-// CTAs 1..: the problem block (prepare_problem) when the state changed or its rows are needed.
+// The 3-LUT scan of lut_search (lut.c:501-523): the first triple (i < k < m, as positions in the
+// caller's shuffled gate order) whose three gates admit SOME 3-input function equal to the target
+// under the mask (check_n_lut_possible(3, ...); get_lut_function then always succeeds).  Runs in the
+// scan blocks of k_begin, on the uncompressed tables (arguments / resident copy), so that it needs
+// nothing the same launch derives.  One warp per position pair (i, k), lanes over m; the minimum of
+// the packed position triple i << 18 | k << 9 | m goes to ctl->best3; the last scan block to finish
+// closes stage 0 (result to the host) and leaves best3 / scan_done as it found them.
+__device__ __forceinline__ void scan3_blocks(const DevProblem *__restrict__ prob,
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const BeginArgs &a, int blk, int nblks,
+    uint32_t *s_full) {
+  __shared__ uint16_t s_order[512];
+  __shared__ uint32_t s_t[8], s_nt[8];
+  __shared__ int s_last;
+  const int n = a.n;
+  for (int i = threadIdx.x; i < n * 8; i += blockDim.x) {
+    s_full[i] = arg_or_resident(prob, a, i >> 3, i & 7);
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_order[i] = a.order3[i];
+  if (threadIdx.x < 8) {
+    s_t[threadIdx.x] = a.mask[threadIdx.x] & a.target[threadIdx.x];
+    s_nt[threadIdx.x] = a.mask[threadIdx.x] & ~a.target[threadIdx.x];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const uint32_t pairs = (uint32_t)(n * (n - 1) / 2);
+  for (uint32_t pq = (uint32_t)(blk * warps + (threadIdx.x >> 5)); pq < pairs;
+       pq += (uint32_t)(nblks * warps)) {
+    int pi, pk;
+    unrank_pair(pq, n, pi, pk);
+    const unsigned long long key0 = ((unsigned long long)pi << 18) | ((unsigned long long)pk << 9);
+    if (volatile_load(&ctl->best3) < key0) break;   // an earlier triple already matched
+    const uint32_t *ta = s_full + 8 * s_order[pi], *tb = s_full + 8 * s_order[pk];
+    for (int m0 = pk + 1; m0 < n; m0 += 32) {
+      const int pm = m0 + lane;
+      const uint32_t *tc = s_full + 8 * s_order[pm < n ? pm : pk];
+      uint32_t ones[8], zeros[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) ones[c] = zeros[c] = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) {
+        const uint32_t va = ta[w], vb = tb[w], vc = tc[w];
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint32_t ab = ((c & 4) ? va : ~va) & ((c & 2) ? vb : ~vb);   // warp-uniform
+          const uint32_t cell = ab & ((c & 1) ? vc : ~vc);
+          ones[c] |= cell & s_t[w];
+          zeros[c] |= cell & s_nt[w];
+        }
+      }
+      bool ok = pm < n;
+#pragma unroll
+      for (int c = 0; c < 8; c++) ok &= !(ones[c] != 0 && zeros[c] != 0);
+      const uint32_t hit = __ballot_sync(kFull, ok);
+      if (hit != 0) {
+        if (lane == 0) {
+          atomicMin(&ctl->best3, key0 | (unsigned long long)(m0 + __ffs(hit) - 1));
+        }
+        break;   // later m of this pair are larger
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&ctl->scan_done, 1u) == (unsigned int)(nblks - 1);
+  }
+  __syncthreads();
+  if (s_last != 0 && threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long key = volatile_load(&ctl->best3);
+    out->key[0] = key;
+    out->swept[0] = 0;
+    out->feasible[0] = 0;
+    out->overflow[0] = 0;
+    if (key != ~0ull) ctl->found = (a.seq << 8) | 3ull;   // the rest of the chain returns at once
+    ctl->best3 = ~0ull;
+    ctl->scan_done = 0;
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long *>(&out->seq[0]) = a.seq;
+  }
+}
+
+// First kernel of every chain, three kinds of blocks:
+//   block 0: control words, position tables, ticket-group counters, and minpos3 (see DevParams7) by
+//            dynamic programming over the number of unconstrained bits: an entry with a free bit j
+//            is the minimum of the two entries that force bit j (entries are visited level by level
+//            through DevTables::m3_info, which lists them by number of free bits);
+//   then prep_blocks blocks: the problem block (prepare_problem) when the state changed or its
+//            rows are needed;
+//   then the scan blocks: the 3-LUT scan (scan3_blocks), when the call asks for it.
 __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, DevParams7 *__restrict__ par, uint8_t *__restrict__ pos5,
-    uint16_t *__restrict__ order3, uint32_t *__restrict__ gcount,
-    const DevTables *__restrict__ tab, const BeginArgs a) {
+    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, DevParams7 *__restrict__ par,
+    uint8_t *__restrict__ pos5, uint32_t *__restrict__ gcount, const DevTables *__restrict__ tab,
+    int prep_blocks, const BeginArgs a) {
+  extern __shared__ uint32_t smem[];
   if (blockIdx.x != 0) {
-    prepare_problem(prob, a, blockIdx.x - 1, gridDim.x - 1);
+    const int b = (int)blockIdx.x - 1;
+    if (b < prep_blocks) {
+      prepare_problem(prob, a, b, prep_blocks);
+    } else {
+      scan3_blocks(prob, ctl, out, a, b - prep_blocks, (int)gridDim.x - 1 - prep_blocks, smem);
+    }
     return;
   }
   __shared__ uint8_t posm[256];
   __shared__ uint8_t s_min[kMinpos3 + 3];
-  __shared__ uint32_t s_info[kMinpos3];
+  uint32_t *s_info = smem;   // kMinpos3 words
   __shared__ int s_level[10];
   // the visiting order of minpos3 (26 KB): all loads in flight at once, instead of one dependent
   // round trip to L2 per level of the sweep below
@@ -1389,7 +1499,6 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
       ctl->best = ~0ull;
       ctl->ticket2 = 0;
       ctl->ctas_done = 0;
-      ctl->stage_found = 0;
       ctl->overflow = 0;
       ctl->skip7 = 0;
       ctl->seq = a.seq;
@@ -1405,7 +1514,6 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
       ctl->overflow = 0;
       ctl->list_count = 0;
       ctl->ctas_done = 0;
-      ctl->stage_found = 0;
       ctl->skip5 = (a.flags & kBeginSearch5) ? 0u : 1u;
       ctl->skip7 = (a.flags & kBeginSearch7) ? 0u : 1u;
     }
@@ -1415,9 +1523,6 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
   }
   if (a.flags & kBeginSearch5) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) pos5[i] = a.pos5[i];
-  }
-  if (a.flags & kBeginOrder3) {
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) order3[i] = a.order3[i];
   }
   if (!(a.flags & kBeginSearch7)) return;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -1443,66 +1548,6 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
     __syncthreads();
   }
   for (int e = threadIdx.x; e < kMinpos3; e += blockDim.x) par->minpos3[e] = s_min[e];
-}
-
-// ------------------------------------------------------------------------------------------------
-// The 3-LUT scan of lut_search (lut.c:501-523): the first triple (i < k < m, as positions in the
-// caller's shuffled gate order) whose three gates admit SOME 3-input function equal to the target
-// under the mask (check_n_lut_possible(3, ...); get_lut_function then always succeeds).  One thread
-// per triple, tickets in order, minimum rank of the position triple in ctl->best; closes stage 0.
-template <int NW>
-__global__ void __launch_bounds__(kThreads) k_scan3(const DevProblem *__restrict__ prob,
-    DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const uint16_t *__restrict__ order3) {
-  extern __shared__ uint32_t smem[];
-  wait_for_predecessor();
-  const int n = prob->n;
-  const int npad = (n + 3) & ~3;
-  uint32_t *s_tabs = smem;
-  uint16_t *s_order = reinterpret_cast<uint16_t *>(smem + NW * npad);
-  stage_tables(s_tabs, prob, NW, npad);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s_order[i] = order3[i];
-  __syncthreads();
-  uint32_t T[NW], M[NW];
-#pragma unroll
-  for (int w = 0; w < NW; w++) {
-    T[w] = prob->T[w];
-    M[w] = prob->M[w];
-  }
-  const uint64_t total = c_binom[n][3];
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (uint64_t)gridDim.x * blockDim.x) {
-    if (volatile_load(&ctl->best) < t) break;   // a smaller triple already matched
-    int pos[3];
-    uint64_t unused;
-    unrank_prefix<3, 3>(t, n, pos, unused);
-    const int ga = s_order[pos[0]], gb = s_order[pos[1]], gc = s_order[pos[2]];
-    uint32_t ones[8], zeros[8];
-#pragma unroll
-    for (int c = 0; c < 8; c++) ones[c] = zeros[c] = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-      const uint32_t ta = s_tabs[w * npad + ga], tb = s_tabs[w * npad + gb],
-          tc = s_tabs[w * npad + gc];
-#pragma unroll
-      for (int c = 0; c < 8; c++) {
-        const uint32_t cell = M[w] & ((c & 4) ? ta : ~ta) & ((c & 2) ? tb : ~tb)
-            & ((c & 1) ? tc : ~tc);
-        ones[c] |= cell & T[w];
-        zeros[c] |= cell & ~T[w];
-      }
-    }
-    bool ok = true;
-#pragma unroll
-    for (int c = 0; c < 8; c++) ok &= !(ones[c] != 0 && zeros[c] != 0);
-    if (ok) {
-      atomicMin(&ctl->best, (unsigned long long)t);
-      break;   // this thread's later triples are larger
-    }
-  }
-  let_successor_start();
-  if (last_cta_of_grid(ctl) && threadIdx.x == 0) {
-    close_stage(ctl, out, 0, volatile_load(&ctl->best), 0, 0, 0);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1563,14 +1608,130 @@ __device__ __forceinline__ void tuple_summary(const uint32_t *s_tabs, int npad, 
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Phase 2, stage 1 as a FILTER with one lane per outer triple.
+//
+// For an outer triple the 128 cells of the tuple's summary fall into 8 groups of 16 (one group per
+// pattern u of the three outer gates, 16 cells over the other four gates).  An outer function fo is
+// a 2-colouring of the groups; it leaves a decomposable remainder iff no two groups of the same
+// colour hold, in the same place, one a masked 1 and the other a masked 0 -- i.e. iff fo properly
+// 2-colours the "conflict graph" on the 8 groups.  Most (tuple, outer triple) pairs have NO proper
+// colouring (measured on bench.py's states: 87-100 %), and deciding that needs neither the order of
+// the groups nor the order of the cells inside them.  So lane j < 25 takes outer triple j of the
+// warp's tuple: it permutes the summary's index bits (at most two word<->bit exchanges, done
+// without branches since every lane has its own triple) until the three outer gates select (word,
+// half word), tests the 28 pairs of groups with one AND each, and ANDs a 128-bit set of colourings
+// (those with group 7 = 0; the set is closed under complement) with one mask per conflict.  About
+// 350 warp instructions decide all 25 triples of a tuple; the ballot form below (~170 per triple)
+// only sees the triples that pass.
+//
+// Summary layout (tuple_summary): word = f << 1 | g, bit = a << 4 | b << 3 | c << 2 | d << 1 | e.
+
+// Exchanges index bit i (inside the words) with word-index bit wb of a 4-word set; on == false
+// makes it a no-op.  Branch-free: i, wb and on differ from lane to lane.
+__device__ __forceinline__ void swap_bit_with_word(uint32_t *h, int i, int wb, bool on) {
+  uint32_t m = i == 0 ? 0x55555555u : i == 1 ? 0x33333333u : i == 2 ? 0x0f0f0f0fu : 0x00ff00ffu;
+  if (!on) m = 0;
+  const int d = 1 << i;
+  // word pairs: wb == 0: (0,1) (2,3); wb == 1: (0,2) (1,3) -- bring them to the first form
+  const uint32_t a1 = wb ? h[2] : h[1];
+  const uint32_t a2 = wb ? h[1] : h[2];
+  uint32_t lo0 = h[0], hi0 = a1, lo1 = a2, hi1 = h[3];
+  uint32_t t = ((lo0 >> d) ^ hi0) & m;
+  hi0 ^= t;
+  lo0 ^= t << d;
+  t = ((lo1 >> d) ^ hi1) & m;
+  hi1 ^= t;
+  lo1 ^= t << d;
+  h[0] = lo0;
+  h[1] = wb ? lo1 : hi0;
+  h[2] = wb ? hi0 : lo1;
+  h[3] = hi1;
+}
+
+// colourings x < 128 as 4 words (x = 32 * wd + bit): those in which group u has colour 1
+__host__ __device__ constexpr uint32_t colour_pattern(int u, int wd) {
+  return u == 0 ? 0xAAAAAAAAu : u == 1 ? 0xCCCCCCCCu : u == 2 ? 0xF0F0F0F0u : u == 3 ? 0xFF00FF00u
+      : u == 4 ? 0xFFFF0000u : u == 5 ? ((wd & 1) ? 0xffffffffu : 0u)
+      : u == 6 ? ((wd & 2) ? 0xffffffffu : 0u) : 0u;
+}
+
+// Bit j of the result: outer triple j (in the order of lut.c:396-415: the 15 triples {a, x, y}, then
+// the 10 triples {b, x, y} without a) of the tuple whose summary is sH[0..7] may have survivors.
+__device__ __forceinline__ uint32_t triples_with_colourings(const uint32_t *sH, int lane) {
+  const int j = lane < 25 ? lane : 0;
+  // the triple's two other positions x < y (1 = b .. 6 = g): pairs in lexicographic order
+  int x, y;
+  {
+    int q = j < 15 ? j : j - 15;
+    x = j < 15 ? 1 : 2;
+    int row = 6 - x;
+#pragma unroll
+    for (int step = 0; step < 4; step++) {
+      const bool more = q >= row;
+      q -= more ? row : 0;
+      x += more ? 1 : 0;
+      row -= more ? 1 : 0;
+    }
+    y = x + 1 + q;
+  }
+  uint32_t h1[4], h0[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    h1[i] = sH[i];
+    h0[i] = sH[4 + i];
+    if (j >= 15) {
+      // the triples with b and without a: exchange index bits 4 (a) and 3 (b) inside the words,
+      // so that b selects the half word; a becomes one of the four inner gates
+      uint32_t t = ((h1[i] >> 8) ^ h1[i]) & 0x0000ff00u;
+      h1[i] ^= t | (t << 8);
+      t = ((h0[i] >> 8) ^ h0[i]) & 0x0000ff00u;
+      h0[i] ^= t | (t << 8);
+    }
+  }
+  // bring x and y to the word-index bits (f = bit 1, g = bit 0 of the word index); the in-word
+  // index bit of position p (1 = b .. 4 = e) is 4 - p.  x goes to f's place unless f is the other
+  // outer gate (then to g's); y, if it is an in-word gate as well, to g's place.
+  const int ix = x <= 4 ? 4 - x : 0, iy = y <= 4 ? 4 - y : 0;
+  swap_bit_with_word(h1, ix, y == 5 ? 0 : 1, x <= 4);
+  swap_bit_with_word(h0, ix, y == 5 ? 0 : 1, x <= 4);
+  swap_bit_with_word(h1, iy, 0, y <= 4);
+  swap_bit_with_word(h0, iy, 0, y <= 4);
+  // group u = word * 2 + half: gx[u] = ones | zeros << 16, gr[u] = zeros | ones << 16
+  uint32_t gx[8], gr[8];
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    gx[2 * w] = __byte_perm(h1[w], h0[w], 0x5410);
+    gx[2 * w + 1] = __byte_perm(h1[w], h0[w], 0x7632);
+    gr[2 * w] = __byte_perm(h0[w], h1[w], 0x5410);
+    gr[2 * w + 1] = __byte_perm(h0[w], h1[w], 0x7632);
+  }
+  uint32_t v[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+#pragma unroll
+    for (int b = a + 1; b < 8; b++) {
+      const uint32_t e = (gx[a] & gr[b]) != 0 ? 0xffffffffu : 0u;   // groups a and b conflict
+#pragma unroll
+      for (int wd = 0; wd < 4; wd++) {
+        const uint32_t differ = colour_pattern(a, wd) ^ colour_pattern(b, wd);
+        v[wd] &= differ | ~e;
+      }
+    }
+  }
+  return __ballot_sync(kFull, lane < 25 && (v[0] | v[1] | v[2] | v[3]) != 0);
+}
+
 template <int NW>
 __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restrict__ prob,
     DevCtl *__restrict__ ctl, HostOut *__restrict__ out, const DevParams7 *__restrict__ par,
-    const uint64_t *__restrict__ list, int part, int nparts, const DevTables *__restrict__ tab) {
+    const uint64_t *__restrict__ list, int part, int nparts, const DevTables *__restrict__ tab,
+    int use_filter) {
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_minpos[kMinpos3 + 3];
   __shared__ uint16_t s_p3[256];
-  __shared__ uint8_t s_pos[256];
+  __shared__ uint8_t s_pos[256];         // outer function -> its position in the shuffled order
+  __shared__ uint8_t s_ord[256];         // position -> outer function
   __shared__ uint8_t s_fo[kWarpsPerCta][256];
   __shared__ uint32_t s_src7[25 * 32];   // copy of DevTables::src7
   __shared__ uint32_t s_H[kWarpsPerCta][24];
@@ -1595,14 +1756,18 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
 
   // the list length is on the device (k_offsets / k_merge_runs); this part's share is
   // ceil((count - part) / nparts) entries, surplus CTAs have nothing to do
-  const bool skip = volatile_load32(&ctl->stage_found) != 0 || volatile_load32(&ctl->skip7) != 0
+  const bool skip = chain_is_over(ctl) || volatile_load32(&ctl->skip7) != 0
       || volatile_load32(&ctl->overflow) != 0;
   const unsigned int count = skip ? 0u : ctl->list_count;
   const unsigned int share = count > (unsigned int)part
       ? (count - (unsigned int)part + (unsigned int)nparts - 1) / (unsigned int)nparts : 0u;
   if (blockIdx.x * kWarpsPerCta < share) {
   for (int i = threadIdx.x; i < kMinpos3; i += blockDim.x) s_minpos[i] = par->minpos3[i];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = par->pos_outer[i];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    const uint8_t po = par->pos_outer[i];
+    s_pos[i] = po;
+    s_ord[po] = (uint8_t)i;
+  }
   __syncthreads();
 
   uint32_t T[NW], M[NW];
@@ -1638,6 +1803,10 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
       sub = (int)((prev >> 45) & 0x1ffu);
     }
     tuple_summary<NW>(s_tabs, npad, g, T, M, lane, sH);
+    // outer triples worth the ballot form (all of them for a stale-cache tuple, whose first triple
+    // is decided on a second summary)
+    const uint32_t pass_i = (use_filter != 0 && !stale) ? triples_with_colourings(sH, lane)
+                                                        : 0x1ffffffu;
     if (stale) {
       int g2[7];
 #pragma unroll
@@ -1649,6 +1818,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
     bool found = false;
     uint64_t key = 0;
     for (int j = 0; j < 25 && !found; j++) {
+      if (((pass_i >> j) & 1u) == 0) continue;   // the filter found no admissible outer function
       const uint32_t *Hs = (stale && j == 0) ? sH + 8 : sH;
       const uint32_t srcw = s_src7[j * 32 + lane];
       uint32_t P1[4], P0[4];
@@ -1688,6 +1858,10 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
         any |= sv;
         if (lane == hi) my_surv = sv;
       }
+#ifdef SBG_COUNT_STAGE1
+      if (lane == 0) atomicAdd(&ctl->pad0[0], 1ull);                    // (tuple, outer triple) pairs
+      if (lane == 0 && any != 0) atomicAdd(&ctl->pad0[1], 1ull);        // ... with survivors
+#endif
       if (any == 0) continue;  // no outer function leaves a conflict-free 5-input remainder
       uint32_t *surv = sH + 16;
       __syncwarp();
@@ -1782,7 +1956,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   }  // this CTA has a share
   let_successor_start();
   if (last_cta_of_grid(ctl) && threadIdx.x == 0
-      && volatile_load32(&ctl->stage_found) == 0 && volatile_load32(&ctl->skip7) == 0) {
+      && !chain_is_over(ctl) && volatile_load32(&ctl->skip7) == 0) {
     const unsigned long long key = volatile_load(&ctl->best);
     unsigned long long tuple = 0, tuple_prev = 0;
     if (key != ~0ull) {
@@ -1790,6 +1964,11 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
       tuple = list[idx];
       if (idx > 0) tuple_prev = list[idx - 1];
     }
+#ifdef SBG_COUNT_STAGE1
+    printf("S1 list %u pairs %llu with_survivors %llu\n", ctl->list_count, ctl->pad0[0], ctl->pad0[1]);
+    ctl->pad0[0] = 0;
+    ctl->pad0[1] = 0;
+#endif
     close_stage(ctl, out, 2, key, ctl->list_count, tuple, tuple_prev);
   }
 }

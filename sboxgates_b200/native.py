@@ -59,6 +59,7 @@ SIGNATURES = {
     "sbg_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_int]),
     "sbg_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "sbg_transfer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "sbg_host_seconds": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sbg_alu_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sbg_search_node": (C.c_int, [C.c_void_p, C.POINTER(SbgJob), C.POINTER(SbgNodeResult)]),
     "sbg_search_batch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(SbgJob),

@@ -35,6 +35,7 @@ engines = {"pm4": engine(SBG_PM_PREFIX=4), "pm5": engine(SBG_PM_PREFIX=5),
            "plain": engine(SBG_PDL=0), "pm4_b1": engine(SBG_PM_PREFIX=4, SBG_BATCH=1),
            "pm5_b16": engine(SBG_PM_PREFIX=5, SBG_BATCH=16)}
 e5 = {"fused": engine(SBG_SEARCH5="fused"), "two": engine(SBG_SEARCH5="two")}
+e7_plain = engine(SBG_DECOMP_FILTER=0)   # phase 2 without the lane-parallel stage-1 filter
 sbox = S.rijndael_sbox()
 t_start = time.time()
 stats = {"cases": 0, "oracle_lists": 0, "oracle_searches": 0, "hits": 0, "found5": 0, "found7": 0}
@@ -90,7 +91,9 @@ for ci in range(cases):
     cnt = eng.filter7_keep_local()
     k1 = eng.decomp7_part(0, 1, outer, middle)
     k4 = min(eng.decomp7_part(p, 4, outer, middle) for p in range(4))
-    assert whole.key == k1 == k4, (ci, n, "search7 keys", whole.key, k1, k4)
+    e7_plain.load(tabs, tgt, mask, inb)
+    plain = e7_plain.search7(outer, middle)
+    assert whole.key == k1 == k4 == plain.key, (ci, n, "search7 keys", whole.key, k1, k4, plain.key)
     stats["found7"] += bool(whole.found)
     if n <= 13 and (whole.found or cnt <= 6):
         tuples = np.array([sb.lut.unpack_tuple7(p) for p in ref], dtype=np.uint16).reshape(-1, 7)

@@ -77,6 +77,36 @@ def test_random_vs_oracle(engine):
                 assert res.tuples_feasible == st.tuples_feasible
 
 
+def test_phase2_filter_forms_agree_with_the_oracle(monkeypatch):
+    """Phase 2 decides most (tuple, outer triple) pairs with a filter that gives every outer triple
+    of a tuple a lane of its own (conflict graph of the 8 outer patterns, 2-colourable or not) and
+    the rest with the warp-cooperative ballot form; SBG_DECOMP_FILTER=0 leaves everything to the
+    ballot form.  Either way results must equal the CPU oracle's on recorded reference calls (incl.
+    the stale-cache cases) and on random states."""
+    for mode in ("0", "1"):
+        eng = _fresh_engine(monkeypatch, SBG_DECOMP_FILTER=mode)
+        n_cases = _replay(eng, os.path.join(S.GOLDEN, "ref_cases.bin"))
+        assert n_cases >= 60
+        assert _replay(eng, os.path.join(S.GOLDEN, "run_sodark_seed1.bin")) > 0
+        sbox = S.rijndael_sbox()
+        rs = np.random.RandomState(4242)
+        for i in range(25):
+            n = int(rs.choice([9, 10, 11, 12, 13]))
+            tabs = S.synthetic_state(n, seed=5000 + i)
+            fixed = [(int(b), int(rs.randint(0, 2))) for b in rs.choice(8, int(rs.randint(1, 5)),
+                                                                        replace=False)]
+            mask, inb = S.mux_mask(fixed), [b for b, _ in fixed if b < n]
+            tgt = S.sbox_target(sbox, int(rs.randint(0, 8)))
+            seed = rs.bytes(128)
+            o_rng = S.OrcRng.from_seed(seed)
+            found, ret, st = S.oracle_search(7, tabs, tgt, mask, inb, o_rng)
+            if st.tuples_feasible > 40 and not found:
+                continue   # too slow for the oracle
+            res = sb.search_7lut(eng, tabs, tgt, mask, inb, Xorshift1024(seed))
+            assert (res.found, res.ret) == (found, ret), (mode, i, n, fixed)
+        eng.close()
+
+
 def test_filter7_list_matches_oracle(engine):
     sbox = S.rijndael_sbox()
     for i, (n, fixed) in enumerate([(12, [(0, 1), (3, 0)]), (14, [(1, 1), (2, 1), (6, 0)]),
