@@ -805,10 +805,19 @@ bool valid_order(const uint8_t *order) {
 // in L.d_sorted, its length in *count_out.  Handles the hit buffer overflowing (grow once, then the
 // bounded-parallelism retry) and sweeps with more tickets than the ticket table holds (several
 // launches, each appending to the list: later tickets only hold larger tuples).
-int run_filter7(sbg_handle *h, sbg_lane &L, int part, int nparts, uint32_t *count_out) {
+int run_filter7(sbg_handle *h, sbg_lane &L, int part, int nparts, uint32_t *count_out,
+    bool overflowed_already = false) {
   sbg_handle::HostProblem &hp = h->slots[L.slot];
   int rc;
   bool retry = false;
+  if (overflowed_already) {
+    // the caller's own launch (the fused chain) has just overflowed this buffer: do not repeat it
+    if (!h->hits_cap_forced && L.hits_cap < kGrownHitsCap) {
+      if ((rc = ensure_hits(h, L, kGrownHitsCap)) != SBG_OK) return rc;
+    } else {
+      retry = true;
+    }
+  }
   uint64_t seg_base = 0, swept = 0;
   uint32_t list_base = 0;
   float ms_filter = 0.f, ms_order = 0.f;
@@ -1125,10 +1134,11 @@ int redo_search5_fused(sbg_handle *h, sbg_lane &L, const uint8_t *order5) {
 }
 
 // search_7lut of the lane's problem through the step-by-step path (overflow handling, segments).
-int redo_search7_steps(sbg_handle *h, sbg_lane &L, const uint8_t *outer, const uint8_t *middle) {
+int redo_search7_steps(sbg_handle *h, sbg_lane &L, const uint8_t *outer, const uint8_t *middle,
+    bool hit_buffer_overflowed) {
   int rc;
   uint32_t keep = 0;
-  if ((rc = run_filter7(h, L, 0, 1, &keep)) != SBG_OK) return rc;
+  if ((rc = run_filter7(h, L, 0, 1, &keep, hit_buffer_overflowed)) != SBG_OK) return rc;
   L.list_count = keep;
   L.list_ready = true;
   L.seq++;
@@ -1180,7 +1190,7 @@ int collect_chain(sbg_handle *h, sbg_lane &L, const sbg_job *job, const ChainInf
     }
     if (redone && (job->flags & kDoSearch7) && hp.n >= 7) {
       // the chain's 7-LUT stage was cancelled together with the incomplete 5-LUT stage
-      if ((rc = redo_search7_steps(h, L, job->outer7, job->middle7)) != SBG_OK) return rc;
+      if ((rc = redo_search7_steps(h, L, job->outer7, job->middle7, false)) != SBG_OK) return rc;
       redone7 = true;
     }
   }
@@ -1189,7 +1199,8 @@ int collect_chain(sbg_handle *h, sbg_lane &L, const sbg_job *job, const ChainInf
     h->d2h_bytes += 64;
     uint64_t swept7 = o->swept[2];
     if (o->overflow[2] != 0 || redone7) {
-      if (!redone7 && (rc = redo_search7_steps(h, L, job->outer7, job->middle7)) != SBG_OK) return rc;
+      if (!redone7 && (rc = redo_search7_steps(h, L, job->outer7, job->middle7,
+          o->overflow[2] == 1)) != SBG_OK) return rc;
       swept7 = h->swept;
     }
     L.list_count = (uint32_t)o->feasible[2];

@@ -1,6 +1,6 @@
 #!/bin/bash
-# Quick GPU check after a kernel change: node + parity tests, drop-in timing, headline bench.
+# Quick GPU check after a kernel change: parity + node + stress tests, drop-in timing, headline bench.
 cd /root/repo
-( timeout 1500 python -m pytest tests/test_gpu_node.py tests/test_gpu_parity.py tests/test_dropin_gpu.py -m gpu -x -q 2>&1 | tail -6 )
+( timeout 1800 python -m pytest tests/test_gpu_node.py tests/test_gpu_parity.py tests/test_gpu_stress.py -m gpu -x -q 2>&1 | tail -6 )
 bash scripts/dropin_time.sh sboxgates_gpu 2>&1 | grep -v "^\[sbg\] start-up" | cut -c1-330
-bash scripts/ab_bench.sh sboxgates_b200/libsboxgates_b200.so
+bash scripts/ab_bench.sh sboxgates_b200/libsboxgates_b200.so sboxgates_b200/libsboxgates_b200.so:SBG_BALANCED5=0
