@@ -187,6 +187,7 @@ struct sbg_handle {
   int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   int opt_pdl = 1;          // SBG_PDL: programmatic dependent launch between the kernels of a chain
   int opt_speculate = 1;    // SBG_SPECULATE: see enqueue_chain
+  int opt_packed = 1;       // SBG_PACKED: phase 1 keeps two parts per register where <= 15 last gates remain
   int opt_decomp_filter = 1;  // SBG_DECOMP_FILTER: lane-parallel stage-1 filter of phase 2 (0 = ballot form only)
   int opt_batch_conc = 2;   // SBG_BATCH_CONC: phase-1 prefixes per ticket while several chains share
                             // the device (sbg_search_batch)
@@ -475,22 +476,28 @@ double wall_now() {
 // for `stage`.  No CUDA call on the fast path; every ~2 ms of waiting the stream is queried so that
 // a failed launch turns into an error instead of a hang.
 int wait_stage(sbg_handle *h, sbg_lane &L, int stage) {
+  // stage 0 (the 3-LUT scan) publishes seq << 28 | key in one word, see scan3_blocks
   volatile unsigned long long *flag = &L.h_out->seq[stage];
+  const int shift = stage == 0 ? kScanKeyBits : 0;
   uint64_t spins = 0;
   const double t_wait = wall_now();
-  while (*flag != L.seq) {
+  while ((*flag >> shift) != L.seq) {
     __builtin_ia32_pause();
     if ((++spins & 0x3ffff) == 0) {
       const cudaError_t e = cudaStreamQuery(L.stream);
       if (e != cudaSuccess && e != cudaErrorNotReady) {
         return fail(h, SBG_ERR_CUDA, "search chain failed: %s", cudaGetErrorString(e));
       }
-      if (e == cudaSuccess && *flag != L.seq) {
+      if (e == cudaSuccess && (*flag >> shift) != L.seq) {
         return fail(h, SBG_ERR_STATE, "internal: chain ended without publishing stage %d", stage);
       }
     }
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  if (stage == 0) {
+    const unsigned long long key = *flag & kScanKeyNone;
+    L.h_out->key[0] = key == kScanKeyNone ? SBG_KEY_NONE : key;
+  }
   h->wait_s[stage] += wall_now() - t_wait;
   return SBG_OK;
 }
@@ -679,7 +686,8 @@ int launch_filter7_pm_p(sbg_handle *h, sbg_lane &L, const FilterPlan &fp, int pa
         (unsigned long long)L.hits_cap, (unsigned long long)fp.tickets_cap, part, nparts,      \
         list_cap, (int)fp.batch, fp.max_warps,                                                 \
         pl.all ? (unsigned long long)fp.total : pl.t_offset, pl.items, std::max(1, pl.chunks), \
-        (unsigned long long)fp.chunk_tickets, (unsigned long long)fp.seg_base);                \
+        (unsigned long long)fp.chunk_tickets, (unsigned long long)fp.seg_base,                 \
+        h->opt_packed ? 15 : 0);                                                               \
   }
   const bool shifted = P == 4 && (h->opt_shift >= 0 ? h->opt_shift != 0 && n <= 63
                                                      : n <= kShiftMaxGates);
@@ -1070,7 +1078,9 @@ int enqueue_chain(sbg_handle *h, sbg_lane &L, int what, const CallInputs &in, Ch
     if ((rc = wait_stage(h, L, 0)) != SBG_OK) return rc;
   }
   auto over = [&]() {
-    return (flags & kBeginScan3) && o->seq[0] == L.seq && o->key[0] != SBG_KEY_NONE;
+    const unsigned long long word = o->seq[0];   // seq << 28 | key, see scan3_blocks
+    return (flags & kBeginScan3) && (word >> kScanKeyBits) == L.seq
+        && (word & kScanKeyNone) != kScanKeyNone;
   };
   if ((flags & kBeginSearch5) && !over()
       && (rc = enqueue_search5(h, L, 0, 1, ci.two5)) != SBG_OK) return rc;
@@ -1423,6 +1433,7 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_BATCH") != nullptr) h->opt_batch = atoi(getenv("SBG_BATCH"));
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
   if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
+  if (getenv("SBG_PACKED") != nullptr) h->opt_packed = atoi(getenv("SBG_PACKED")) != 0;
   if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;
   if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));
   if (getenv("SBG_PDL") != nullptr) h->opt_pdl = atoi(getenv("SBG_PDL")) != 0;

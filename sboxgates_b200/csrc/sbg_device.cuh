@@ -17,12 +17,14 @@
 // per-launch DRAM traffic is the 16.5 KB problem block plus the hit list.
 #pragma once
 
-#ifdef SBG_COUNT_STAGE1
+#if defined(SBG_COUNT_STAGE1) || defined(SBG_COUNT_FILTER)
 #include <cstdio>
 #endif
 #include <cuda_pipeline.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 namespace sbg {
 
@@ -156,22 +158,64 @@ __device__ __forceinline__ void stage_tables(uint32_t *s_tabs, const DevProblem 
   __syncthreads();
 }
 
-// Work item t of the P-element prefixes of K-combinations over n gates, lexicographic order.
-// Also returns the rank (in C(n,K) order, lut.c:635-662) of the first combination with that prefix.
-template <int P, int K>
-__device__ __forceinline__ void unrank_prefix(uint64_t t, int n, int *pre, uint64_t &base_rank) {
+// Work item t of the P-element prefixes of K-combinations over n gates, lexicographic order, and
+// (RANK) the rank in C(n,K) order (lut.c:635-662) of the first combination with that prefix.
+// C(a, r) for 0 <= a <= 512, r <= 5, by arithmetic (exact at every step: a product of k consecutive
+// integers is divisible by k!).  r is a compile-time constant wherever this is called from an
+// unrolled loop, the chain below then folds to the one case.  The table c_binom sits in constant
+// memory, which serves one address per warp at a time -- lanes that each need a different entry
+// compute it instead.
+__device__ __forceinline__ uint64_t binom_arith(uint32_t a, int r) {
+  if (r <= 0) return 1ull;
+  if (r == 1) return a;
+  const uint32_t c2 = (a * (a - 1u)) >> 1;                 // <= 130,816
+  if (r == 2) return c2;
+  const uint32_t c3 = (c2 * (a - 2u)) * 0xaaaaaaabu;       // exact division by 3 (inverse mod 2^32)
+  if (r == 3) return c3;
+  const uint64_t c4 = ((uint64_t)c3 * (uint64_t)(a - 3u)) >> 2;
+  if (r == 4) return c4;                                   // (a < r: some factor above is zero)
+  return (c4 * (uint64_t)(a - 4u)) / 5ull;
+}
+
+// unrank_prefix by the whole warp: per element, lane l asks "do at most t prefixes have a smaller
+// element here than x0 + l?" -- the number that do is C(np - x0, r) - C(np - y, r) with r elements
+// still to place (hockey stick) -- and one ballot counts the lanes that say yes.  Three or four
+// ballots instead of a loop that walks the gates one constant-memory load at a time (which was a
+// tenth of phase 1's instructions at n = 40).  All lanes must call; all receive the result.
+template <int P, int K, bool RANK>
+__device__ __forceinline__ void unrank_prefix_warp(uint64_t t64, int n, int *pre, uint64_t &base_rank,
+    int lane) {
+  static_assert(P <= 5 && (!RANK || K <= 5), "binom_arith covers r <= 5");
+  // the number of P-prefixes fits 32 bits up to P = 4 (C(509, 4) = 2.77e9)
+  using T = typename std::conditional<(P <= 4), uint32_t, uint64_t>::type;
   const int np = n - (K - P);
-  int x = 0;
+  T t = (T)t64;
+  int x0 = 0;
   base_rank = 0;
 #pragma unroll
   for (int pos = 0; pos < P; pos++) {
-    for (;; x++) {
-      const uint64_t cnt = c_binom[np - x - 1][P - pos - 1];
-      if (t < cnt) break;
-      t -= cnt;
-      base_rank += c_binom[n - x - 1][K - pos - 1];
+    const int r = P - pos;
+    int e;
+    if (r == 1) {
+      e = x0 + (int)t;
+    } else {
+      const T total = (T)binom_arith((uint32_t)(np - x0), r);
+      int cnt = 0;
+      for (int y0 = x0;; y0 += 32) {
+        const int y = y0 + lane;
+        const bool le = y <= np - r && (T)(total - (T)binom_arith((uint32_t)max(np - y, 0), r)) <= t;
+        const uint32_t bal = __ballot_sync(kFull, le);
+        cnt += __popc(bal);
+        if (bal != 0xffffffffu) break;
+      }
+      e = x0 + cnt - 1;
+      t -= (T)(total - (T)binom_arith((uint32_t)(np - e), r));
     }
-    pre[pos] = x++;
+    if (RANK) {
+      base_rank += binom_arith((uint32_t)(n - x0), K - pos) - binom_arith((uint32_t)(n - e), K - pos);
+    }
+    pre[pos] = e;
+    x0 = e + 1;
   }
 }
 
@@ -358,9 +402,9 @@ __device__ __forceinline__ uint32_t decomp5_tuple(const uint32_t *s_tabs, int np
 // changes the code of the sweep loop around it for the worse.
 template <int P, int K>
 __device__ __noinline__ void chunk_ticket_prefix(uint64_t t, int n, uint32_t inmask, int *pre,
-    uint64_t &prefix_rank, uint64_t &base_rank) {
+    uint64_t &prefix_rank, uint64_t &base_rank, int lane) {
   uint64_t unused_rank;
-  unrank_prefix<P, K>(t, n - __popc(inmask & 0xffu), pre, unused_rank);
+  unrank_prefix_warp<P, K, false>(t, n - __popc(inmask & 0xffu), pre, unused_rank, lane);
   prefix_rank = 0;
   base_rank = 0;
   int prev = -1;
@@ -450,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       q_limit = q_begin + 32u;
       fetch();
       chunk_ticket_prefix<P, K>(dealt / (uint64_t)chunks_per_prefix, n, inmask, pre, t_first,
-          base_rank);
+          base_rank, lane);
       t_end = t_first + 1;
       if (t_first > stop_at) break;
     } else {
@@ -459,7 +503,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
       if (t_first > stop_at) break;
       fetch();
       t_end = min(t_first + (uint64_t)batch, total);
-      unrank_prefix<P, K>(t_first, n, pre, base_rank);
+      unrank_prefix_warp<P, K, true>(t_first, n, pre, base_rank, lane);
     }
    for (uint64_t gt = t_first; gt < t_end && !warp_finished; gt++) {
     if (gt != t_first) {
@@ -707,7 +751,8 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     uint32_t *__restrict__ tcount, uint32_t *__restrict__ gcount, unsigned long long hits_cap,
     unsigned long long tickets_cap, int part, int nparts, unsigned long long list_cap, int batch,
     int max_warps, unsigned long long t_offset, unsigned long long chunk_items,
-    int chunks_per_prefix, unsigned long long chunk_tickets, unsigned long long seg_base) {
+    int chunks_per_prefix, unsigned long long chunk_tickets, unsigned long long seg_base,
+    int packed_gates) {
   constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
   // Work is handed out through one ordered ticket counter, in lexicographic order, under one stop
@@ -858,7 +903,7 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     if (valid) {
     int pre[P];
     uint64_t unused_rank;
-    unrank_prefix<P, K>(t_first, chunked ? n_allowed : n, pre, unused_rank);
+    unrank_prefix_warp<P, K, false>(t_first, chunked ? n_allowed : n, pre, unused_rank, lane);
     if (chunked) {   // index among the allowed gates -> gate number (excluded gates are < 8)
 #pragma unroll
       for (int i = 0; i < P; i++) {
@@ -916,16 +961,35 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
         __syncwarp();
       }
       const int mc = __popc(mixed_ballot);
+#ifdef SBG_COUNT_FILTER
+      unsigned long long dbg_chunks = 0, dbg_windows = 0, dbg_cells = 0, dbg_pos = 0, dbg_packed = 0;
+      unsigned long long dbg_mc = (unsigned long long)mc;
+#endif
 
       unsigned long long emitted = 0;
       bool prefix_done = false;
       int built = -1;   // SH: window whose shifted rows are in sx
+      // the lane's pair (e, f) = (last+1+run_i, last+1+run_j): unranked once (square root), then
+      // moved on by 32 places per chunk
+      int run_i = 0, run_j = 1;
+      if (P == 4 && q_begin + (uint32_t)lane < Q) unrank_pair(q_begin + (uint32_t)lane, r, run_i, run_j);
       for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !prefix_done; q0 += 32) {
         const uint32_t q = q0 + lane;
         bool lane_ok = q < Q;
+#ifdef SBG_COUNT_FILTER
+        dbg_chunks++;
+#endif
         int pi = 0, pj = 0;
         if (P == 4) {
-          unrank_pair(lane_ok ? q : 0u, r, pi, pj);
+          if (q0 != q_begin) {
+            run_j += 32;
+            while (run_j >= r && run_i < r - 2) {   // into the next row(s): row i holds j = i+1 .. r-1
+              run_i++;
+              run_j += run_i + 1 - r;
+            }
+          }
+          pi = lane_ok ? run_i : 0;   // lanes past the end read the tables of pair (0, 1)
+          pj = lane_ok ? run_j : 1;
         } else {
           pj = lane_ok ? (int)q : 0;
         }
@@ -940,8 +1004,13 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
         // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
         // (SH: windows of 31 gates starting AT the smallest possible g, wb counts them)
         const int first_g = last + (K - P);
+        // PACKED (SH only): a prefix with at most 15 candidate last gates keeps TWO parts in one
+        // accumulator register -- halves of 15 gates + the target bit each, the shifted rows stored
+        // twice over -- so a position costs 2 part masks + 4 accumulates instead of 4 + 8.
+        const bool packed = SH && n - first_g <= packed_gates;   // 15, or 0 = never
         const int wb0 = SH ? 0 : ((first_g >> 5) & ~(W - 1));
         int nvw = 0;      // words of surviving-g vectors stored for this chunk
+        bool chunk_live = false;   // some lane kept a candidate in some window
         for (int wb = wb0; SH ? (first_g + 31 * wb < n) : (wb < ((n + 31) >> 5)); wb += W) {
           const int base = SH ? first_g + 31 * wb : 0;
           uint32_t V[W];
@@ -952,7 +1021,8 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
                 const uint32_t lo = s_xr[pp * ngw], hi = s_xr[pp * ngw + 1];
                 const uint32_t tb = (n <= 31 ? lo : hi) & 0x80000000u;   // the row's target bit
                 const uint32_t v = base < 32 ? __funnelshift_r(lo, hi, base) : (hi >> (base - 32));
-                sx[pp] = (v & 0x7fffffffu) | tb;
+                const uint32_t half = (v & 0x7fffu) | (tb >> 16);
+                sx[pp] = packed ? (half | (half << 16)) : ((v & 0x7fffffffu) | tb);
               }
               __syncwarp();
               built = wb;
@@ -978,8 +1048,60 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
           bool alive = false;
 #pragma unroll
           for (int j = 0; j < W; j++) alive |= V[j] != 0;
-          for (int cj = 0; cj < mc; cj++) {
-            if (!__any_sync(kFull, alive)) break;
+#ifdef SBG_COUNT_FILTER
+          dbg_windows++;
+          if (packed) dbg_packed++;
+#endif
+          bool any_alive = __any_sync(kFull, alive);
+          for (int cj = 0; cj < mc && any_alive; cj++) {
+#ifdef SBG_COUNT_FILTER
+            dbg_cells++;
+            for (int w = 0; w < NW; w++) dbg_pos += __popc(cells[cj * NW + w]);
+#endif
+            if constexpr (SH) {
+              if (packed) {
+                // parts 0 | 1 in the low | high half of (and01, or01), parts 2 | 3 of (and23, or23)
+                uint32_t and01 = 0xffffffffu, or01 = 0u, and23 = 0xffffffffu, or23 = 0u;
+                const uint32_t low_half = 0x0000ffffu ^ ((uint32_t)max_warps >> 31);
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+                  uint32_t bits = cells[cj * NW + w];
+                  const uint32_t tf_w = tab_f[w * npad];
+                  const uint32_t te_w = tab_e[w * npad];
+                  while (bits != 0) {
+                    const int c = clz_nonzero(bits);
+                    bits &= low31 >> c;
+                    const uint32_t fb = (uint32_t)((int32_t)(tf_w << c) >> 31);
+                    const uint32_t eb = (uint32_t)((int32_t)(te_w << c) >> 31);
+                    const uint32_t x = lds_u32(sx_top + (uint32_t)(w * 128) - 4u * (uint32_t)c);
+                    // the half this position's part lives in: f picks the half, e the register
+                    const uint32_t m01 = lop3<0x06>(eb, fb, low_half);   // ~eb & (fb ^ low_half)
+                    const uint32_t m23 = lop3<0x60>(eb, fb, low_half);   //  eb & (fb ^ low_half)
+                    and01 = lop3<0xd0>(and01, x, m01);
+                    or01 = lop3<0xf8>(or01, x, m01);
+                    and23 = lop3<0xd0>(and23, x, m23);
+                    or23 = lop3<0xf8>(or23, x, m23);
+                  }
+                }
+                // per half: admissible g = constant over the part, or the part lacks a target value
+                // (bit 15 of a half: OR = some target 1 seen, AND = only target 1 seen)
+                uint32_t v = V[0];
+                {
+                  const uint32_t z = or01 & ~and01, adm = and01 | ~or01;
+                  v &= (adm | ~(uint32_t)((int32_t)(z << 16) >> 31))
+                      & ((adm >> 16) | ~(uint32_t)((int32_t)z >> 31));
+                }
+                {
+                  const uint32_t z = or23 & ~and23, adm = and23 | ~or23;
+                  v &= (adm | ~(uint32_t)((int32_t)(z << 16) >> 31))
+                      & ((adm >> 16) | ~(uint32_t)((int32_t)z >> 31));
+                }
+                V[0] = v;
+                alive = v != 0;
+                any_alive = __any_sync(kFull, alive);
+                continue;
+              }
+            }
             uint32_t a_and[NP][W], a_or[NP][W];
 #pragma unroll
             for (int k = 0; k < NP; k++) {
@@ -1064,7 +1186,9 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
             alive = false;
 #pragma unroll
             for (int jw = 0; jw < W; jw++) alive |= V[jw] != 0;
+            any_alive = __any_sync(kFull, alive);
           }
+          chunk_live |= any_alive;
           // park this window's survivors; the chunk is emitted once all its windows are done, so
           // that a lane's hits come out in increasing g whatever the window they were found in
 #pragma unroll
@@ -1072,9 +1196,9 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
           nvw += W;
         }
         // emit the chunk: lane-major (= (e,f) order), then g ascending
+        if (!chunk_live) continue;   // the common case: nothing survived
         int cnt = 0;
         for (int i = 0; i < nvw; i++) cnt += __popc(vs[i * 32 + lane]);
-        if (!__any_sync(kFull, cnt != 0)) continue;   // the common case: nothing survived
         int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -1118,6 +1242,17 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
         // between chunks, when every pair up to here has all its g emitted.
         if (emitted >= list_cap) prefix_done = true;
       }
+#ifdef SBG_COUNT_FILTER
+      if (lane == 0) {
+        atomicAdd(&ctl->pad1[0], 1ull);
+        atomicAdd(&ctl->pad1[1], dbg_chunks);
+        atomicAdd(&ctl->pad1[2], dbg_windows);
+        atomicAdd(&ctl->pad1[3], dbg_cells);
+        atomicAdd(&ctl->pad1[4], dbg_pos);
+        atomicAdd(&ctl->pad1[5], dbg_packed);
+        atomicAdd(&ctl->pad1[6], dbg_mc);
+      }
+#endif
     }
     }  // valid
     if (lane == 0) {
@@ -1151,6 +1286,12 @@ __global__ void __launch_bounds__(256) k_offsets(DevCtl *__restrict__ ctl,
     const unsigned long long total = (unsigned long long)list_base
         + min(volatile_load(&ctl->hit_count), (unsigned long long)0xffffffffu);
     ctl->list_count = (unsigned int)min(total, (unsigned long long)list_cap);
+#ifdef SBG_COUNT_FILTER
+    printf("F1 prefixes %llu chunks %llu windows %llu cells %llu positions %llu packed %llu mixed %llu hits %llu\n",
+        ctl->pad1[0], ctl->pad1[1], ctl->pad1[2], ctl->pad1[3], ctl->pad1[4], ctl->pad1[5],
+        ctl->pad1[6], ctl->hit_count);
+    for (int i = 0; i < 7; i++) ctl->pad1[i] = 0;
+#endif
   }
   if (first >= handed) return;
   // hits in front of this group
@@ -1269,6 +1410,8 @@ struct BeginArgs {
   uint32_t mask[8];
   uint32_t newg[kArgGates][8];
 };
+constexpr int kScanKeyBits = 28;                       // stage-0 word: seq << 28 | key
+constexpr unsigned long long kScanKeyNone = (1ull << kScanKeyBits) - 1;
 constexpr uint32_t kBeginScan3 = 1, kBeginSearch5 = 2, kBeginSearch7 = 4, kBeginRows = 8,
     kBeginKeepCtl = 16, kBeginOrder3 = 32, kBeginProblem = 64;
 
@@ -1410,7 +1553,8 @@ __device__ __forceinline__ void scan3_blocks(const DevProblem *__restrict__ prob
     int pi, pk;
     unrank_pair(pq, n, pi, pk);
     const unsigned long long key0 = ((unsigned long long)pi << 18) | ((unsigned long long)pk << 9);
-    if (volatile_load(&ctl->best3) < key0) break;   // an earlier triple already matched
+    // an earlier triple already matched?  Only worth a trip to L2 when a warp has many pairs to go
+    if (pairs > 4096u && volatile_load(&ctl->best3) < key0) break;
     const uint32_t *ta = s_full + 8 * s_order[pi], *tb = s_full + 8 * s_order[pk];
     for (int m0 = pk + 1; m0 < n; m0 += 32) {
       const int pm = m0 + lane;
@@ -1450,15 +1594,13 @@ __device__ __forceinline__ void scan3_blocks(const DevProblem *__restrict__ prob
   if (s_last != 0 && threadIdx.x == 0) {
     __threadfence();
     const unsigned long long key = volatile_load(&ctl->best3);
-    out->key[0] = key;
-    out->swept[0] = 0;
-    out->feasible[0] = 0;
-    out->overflow[0] = 0;
     if (key != ~0ull) ctl->found = (a.seq << 8) | 3ull;   // the rest of the chain returns at once
     ctl->best3 = ~0ull;
     ctl->scan_done = 0;
-    __threadfence_system();
-    *reinterpret_cast<volatile unsigned long long *>(&out->seq[0]) = a.seq;
+    // Stage 0 has one result, the 27-bit key: it travels INSIDE the sequence word (one 8-byte
+    // store, no fence across the bus to order it after anything else).
+    *reinterpret_cast<volatile unsigned long long *>(&out->seq[0]) =
+        (a.seq << kScanKeyBits) | (key == ~0ull ? kScanKeyNone : key);
   }
 }
 
