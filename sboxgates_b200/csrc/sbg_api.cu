@@ -591,7 +591,7 @@ size_t filter_pm_smem(int n, int m, bool shifted = false) {
   const int npad = (n + 3) & ~3;
   const int ngw = (((n + 31) >> 5) + 1) & ~1;
   return sizeof(uint32_t) * (size_t)(NW * npad + ((m * ngw + 3) & ~3)
-      + kWarpsPerCta * ((1 << P) * NW + ngw * 32) + (shifted ? kWarpsPerCta * m : 0));
+      + kWarpsPerCta * ((1 << P) * NW + ngw * 32) + (shifted ? std::max(n - 6, 1) * m : 0));
 }
 
 // Position-major phase 1 (k_filter7_pm): work items are 4- or 5-gate prefixes.  The 5-gate form does

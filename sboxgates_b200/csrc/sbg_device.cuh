@@ -158,8 +158,6 @@ __device__ __forceinline__ void stage_tables(uint32_t *s_tabs, const DevProblem 
   __syncthreads();
 }
 
-// Work item t of the P-element prefixes of K-combinations over n gates, lexicographic order, and
-// (RANK) the rank in C(n,K) order (lut.c:635-662) of the first combination with that prefix.
 // C(a, r) for 0 <= a <= 512, r <= 5, by arithmetic (exact at every step: a product of k consecutive
 // integers is divisible by k!).  r is a compile-time constant wherever this is called from an
 // unrolled loop, the chain below then folds to the one case.  The table c_binom sits in constant
@@ -177,7 +175,9 @@ __device__ __forceinline__ uint64_t binom_arith(uint32_t a, int r) {
   return (c4 * (uint64_t)(a - 4u)) / 5ull;
 }
 
-// unrank_prefix by the whole warp: per element, lane l asks "do at most t prefixes have a smaller
+// Work item t of the P-element prefixes of K-combinations over n gates, lexicographic order, and
+// (RANK) the rank in C(n,K) order (lut.c:635-662) of the first combination with that prefix --
+// unranked by the whole warp: per element, lane l asks "do at most t prefixes have a smaller
 // element here than x0 + l?" -- the number that do is C(np - x0, r) - C(np - y, r) with r elements
 // still to place (hockey stick) -- and one ballot counts the lanes that say yes.  Three or four
 // ballots instead of a loop that walks the gates one constant-memory load at a time (which was a
@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   constexpr int P = 3, K = 5, NC = 1 << P;
   extern __shared__ uint32_t smem[];
   __shared__ uint8_t s_pos[256];
+  __shared__ uint32_t s_TM[16];   // T[0..7], M[0..7]: indexed by a lane-dependent word number
 
   wait_for_predecessor();   // the chain's first kernel derives the problem block
   const int n = prob->n;
@@ -443,6 +444,10 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
   const bool skip = chain_is_over(ctl) || volatile_load32(&ctl->skip5) != 0;
   if (!skip) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pos[i] = pos_of[i];
+  if (threadIdx.x < 16) {
+    const int w = threadIdx.x & 7;
+    s_TM[threadIdx.x] = w < NW ? (threadIdx.x < 8 ? prob->T[w] : prob->M[w]) : 0u;
+  }
   __syncthreads();
 
   uint32_t T[NW], M[NW];
@@ -528,33 +533,46 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     if (rejected) continue;
 
     // Prefix cells: lane = cell index, first prefix gate = most significant bit (lut.c:46-49).
+    // The warp's four groups of 8 lanes share the table words among them (G groups, NWG words each).
     uint32_t mixed_ballot;
     {
-      uint32_t c1[NW], c0[NW];
-      uint32_t ones = 0, zeros = 0;
+      constexpr int G = NW >= 4 ? 4 : NW, NWG = NW / G;
       const int cell = lane & (NC - 1);
+      const int group = (lane >> 3) & (G - 1);
+      uint32_t c1[NWG], c0[NWG];
+      uint32_t ones = 0, zeros = 0;
 #pragma unroll
-      for (int w = 0; w < NW; w++) {
-        uint32_t tt = M[w];
+      for (int k = 0; k < NWG; k++) {
+        const int w = group * NWG + k;
+        uint32_t tt = s_TM[8 + w];
+        const uint32_t tw = s_TM[w];
 #pragma unroll
         for (int i = 0; i < P; i++) {
           const uint32_t tv = s_tabs[w * npad + pre[i]];
           tt &= ((cell >> (P - 1 - i)) & 1) ? tv : ~tv;
         }
-        c1[w] = tt & T[w];
-        c0[w] = tt & ~T[w];
-        ones |= c1[w];
-        zeros |= c0[w];
+        c1[k] = tt & tw;
+        c0[k] = tt & ~tw;
+        ones |= c1[k];
+        zeros |= c0[k];
       }
-      const bool mixed = (lane < NC) && ones != 0 && zeros != 0;
-      mixed_ballot = __ballot_sync(kFull, mixed);
+      if (G >= 2) {
+        ones |= __shfl_xor_sync(kFull, ones, 8);
+        zeros |= __shfl_xor_sync(kFull, zeros, 8);
+      }
+      if (G >= 4) {
+        ones |= __shfl_xor_sync(kFull, ones, 16);
+        zeros |= __shfl_xor_sync(kFull, zeros, 16);
+      }
+      const bool mixed = ones != 0 && zeros != 0;   // the same in every group
+      mixed_ballot = __ballot_sync(kFull, mixed) & ((1u << NC) - 1u);
       __syncwarp();
       if (mixed) {
-        const int slot = __popc(mixed_ballot & lanemask_lt());
+        const int slot = __popc(mixed_ballot & ((1u << cell) - 1u));
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-          cells[slot * 2 * NW + w] = c1[w];
-          cells[slot * 2 * NW + NW + w] = c0[w];
+        for (int k = 0; k < NWG; k++) {
+          cells[slot * 2 * NW + group * NWG + k] = c1[k];
+          cells[slot * 2 * NW + NW + group * NWG + k] = c0[k];
         }
       }
       __syncwarp();
@@ -562,11 +580,21 @@ __global__ void __launch_bounds__(kThreads) k_sweep(const DevProblem *__restrict
     const int mc = __popc(mixed_ballot);
 
     bool warp_done = false;
+    // the lane's pair: unranked once per prefix, then moved on by 32 places per chunk (row i of the
+    // pairs of {0..r-1} holds j = i+1 .. r-1)
+    int run_i = 0, run_j = 1;
+    if (q_begin + (uint32_t)lane < Q) unrank_pair(q_begin + (uint32_t)lane, r, run_i, run_j);
     for (uint32_t q0 = q_begin; q0 < min(Q, q_limit) && !warp_done; q0 += 32) {
       const uint32_t q = q0 + lane;
       bool alive = q < Q;
-      int pi, pj;
-      unrank_pair(alive ? q : 0u, r, pi, pj);
+      if (q0 != q_begin) {
+        run_j += 32;
+        while (run_j >= r && run_i < r - 2) {
+          run_i++;
+          run_j += run_i + 1 - r;
+        }
+      }
+      const int pi = alive ? run_i : 0, pj = alive ? run_j : 1;   // past the end: pair (0, 1)
       const int gf = last + 1 + pi;
       const int gg = last + 1 + pj;
       if ((gf < 8 && ((inmask >> gf) & 1u)) || (gg < 8 && ((inmask >> gg) & 1u))) alive = false;
@@ -786,9 +814,11 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
   uint32_t *cells = s_xr + ((m * ngw + 3) & ~3) + warp * (NC * NW);
   // per warp: the surviving-g vectors of one chunk, word-major (vs[word * 32 + lane])
   uint32_t *vs = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW) + warp * (ngw * 32);
-  uint32_t *sx = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW + ngw * 32) + warp * m;   // SH only
+  // SH only: the shifted rows for EVERY window base 6 .. n-1 (a prefix's first window starts at its
+  // last gate + 3 >= 6), sxt[(base - 6) * m + p]; built once per CTA, read by all its warps
+  uint32_t *sxt = s_xr + ((m * ngw + 3) & ~3) + kWarpsPerCta * (NC * NW + ngw * 32);
   static_assert(!SH || (W == 1 && P == 4 && FS), "shifted windows: one word, 4-gate prefixes, n <= 63");
-  const uint32_t sx_top = (uint32_t)__cvta_generic_to_shared(sx + 31);   // row 31 of word 0
+  const uint32_t sxt_top = (uint32_t)__cvta_generic_to_shared(sxt + 31);   // row 31 of base 6
   const uint32_t xr_base = (uint32_t)__cvta_generic_to_shared(s_xr);
   const uint32_t neg_row_bytes = 0u - (uint32_t)ngw * 4u;   // one multiply-add per address
   // 0x7fffffff held in a register: as a literal the compiler re-creates it at every position
@@ -804,6 +834,21 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     }
   }
   stage_tables(s_tabs, prob, NW, npad);
+  if constexpr (SH) {
+    // Window `base` = gates base .. base+30 in bits 0..30 and the row's target bit on top -- or, where
+    // at most packed_gates gates remain (PACKED, below), 15 gates + the target bit, twice over.
+    for (int base = 6 + warp; base < n; base += kWarpsPerCta) {
+      const bool packed_b = n - base <= packed_gates;
+      for (int pp = lane; pp < m; pp += 32) {
+        const uint32_t lo = s_xr[pp * ngw], hi = s_xr[pp * ngw + 1];
+        const uint32_t tb = (n <= 31 ? lo : hi) & 0x80000000u;   // the row's target bit
+        const uint32_t v = base < 32 ? __funnelshift_r(lo, hi, base) : (hi >> (base - 32));
+        const uint32_t half = (v & 0x7fffu) | (tb >> 16);
+        sxt[(base - 6) * m + pp] = packed_b ? (half | (half << 16)) : ((v & 0x7fffffffu) | tb);
+      }
+    }
+    __syncthreads();
+  }
   // overflow retry: only the first max_warps warps work (bounds the hits in flight)
   if (max_warps > 0 && (int)(blockIdx.x * kWarpsPerCta + warp) >= max_warps) return;
 
@@ -933,30 +978,41 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
         continue;
       }
 
-      // mixed cells of the prefix (lane < NC = cell, first gate most significant)
+      // mixed cells of the prefix (cell = lane mod NC, first gate most significant).  With 16 cells
+      // and several table words the two half-warps take half the words each.
       uint32_t mixed_ballot;
       {
-        uint32_t c[NW];
+        constexpr bool kSplit = NC == 16 && NW >= 2;
+        constexpr int NWH = kSplit ? NW / 2 : NW;
+        const bool upper = kSplit && lane >= 16;
+        const int cell = lane & (NC - 1);
+        const uint32_t *tabs_h = s_tabs + (upper ? NWH * npad : 0);
+        uint32_t c[NWH];
         uint32_t ones = 0, zeros = 0;
 #pragma unroll
-        for (int w = 0; w < NW; w++) {
-          uint32_t tt = M[w];
+        for (int k = 0; k < NWH; k++) {
+          uint32_t tt = upper ? M[kSplit ? k + NWH : k] : M[k];
+          const uint32_t tw = upper ? T[kSplit ? k + NWH : k] : T[k];
 #pragma unroll
           for (int i = 0; i < P; i++) {
-            const uint32_t tv = s_tabs[w * npad + pre[i]];
-            tt &= ((lane >> (P - 1 - i)) & 1) ? tv : ~tv;
+            const uint32_t tv = tabs_h[k * npad + pre[i]];
+            tt &= ((cell >> (P - 1 - i)) & 1) ? tv : ~tv;
           }
-          c[w] = tt;
-          ones |= tt & T[w];
-          zeros |= tt & ~T[w];
+          c[k] = tt;
+          ones |= tt & tw;
+          zeros |= tt & ~tw;
         }
-        const bool mixed = lane < NC && ones != 0 && zeros != 0;
-        mixed_ballot = __ballot_sync(kFull, mixed);
+        if (kSplit) {
+          ones |= __shfl_xor_sync(kFull, ones, 16);
+          zeros |= __shfl_xor_sync(kFull, zeros, 16);
+        }
+        const bool mixed = ones != 0 && zeros != 0;   // both halves of a split warp agree
+        mixed_ballot = __ballot_sync(kFull, mixed) & (NC == 32 ? 0xffffffffu : ((1u << (NC & 31)) - 1u));
         __syncwarp();
         if (mixed) {
-          const int slot = __popc(mixed_ballot & lanemask_lt());
+          const int slot = __popc(mixed_ballot & ((1u << cell) - 1u));
 #pragma unroll
-          for (int w = 0; w < NW; w++) cells[slot * NW + w] = c[w];
+          for (int k = 0; k < NWH; k++) cells[slot * NW + (upper ? NWH : 0) + k] = c[k];
         }
         __syncwarp();
       }
@@ -968,7 +1024,6 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
 
       unsigned long long emitted = 0;
       bool prefix_done = false;
-      int built = -1;   // SH: window whose shifted rows are in sx
       // the lane's pair (e, f) = (last+1+run_i, last+1+run_j): unranked once (square root), then
       // moved on by 32 places per chunk
       int run_i = 0, run_j = 1;
@@ -1004,29 +1059,18 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
         // windows of 32*W candidate gates g, from the first that can hold the smallest possible g
         // (SH: windows of 31 gates starting AT the smallest possible g, wb counts them)
         const int first_g = last + (K - P);
-        // PACKED (SH only): a prefix with at most 15 candidate last gates keeps TWO parts in one
-        // accumulator register -- halves of 15 gates + the target bit each, the shifted rows stored
-        // twice over -- so a position costs 2 part masks + 4 accumulates instead of 4 + 8.
-        const bool packed = SH && n - first_g <= packed_gates;   // 15, or 0 = never
         const int wb0 = SH ? 0 : ((first_g >> 5) & ~(W - 1));
         int nvw = 0;      // words of surviving-g vectors stored for this chunk
         bool chunk_live = false;   // some lane kept a candidate in some window
         for (int wb = wb0; SH ? (first_g + 31 * wb < n) : (wb < ((n + 31) >> 5)); wb += W) {
           const int base = SH ? first_g + 31 * wb : 0;
+          // PACKED (SH only): a window with at most 15 candidate last gates keeps TWO parts in one
+          // accumulator register -- halves of 15 gates + the target bit each, the shifted rows stored
+          // twice over -- so a position costs 2 part masks + 4 accumulates instead of 4 + 8.
+          const bool packed = SH && n - base <= packed_gates;   // 15, or 0 = never
+          const uint32_t sx_top = sxt_top + (uint32_t)((base - 6) * m) * 4u;
           uint32_t V[W];
           if constexpr (SH) {
-            if (built != wb) {   // this warp's shifted rows for the window (one build per prefix, mostly)
-              __syncwarp();
-              for (int pp = lane; pp < m; pp += 32) {
-                const uint32_t lo = s_xr[pp * ngw], hi = s_xr[pp * ngw + 1];
-                const uint32_t tb = (n <= 31 ? lo : hi) & 0x80000000u;   // the row's target bit
-                const uint32_t v = base < 32 ? __funnelshift_r(lo, hi, base) : (hi >> (base - 32));
-                const uint32_t half = (v & 0x7fffu) | (tb >> 16);
-                sx[pp] = packed ? (half | (half << 16)) : ((v & 0x7fffffffu) | tb);
-              }
-              __syncwarp();
-              built = wb;
-            }
             uint32_t v = 0x7fffffffu;                // gates base .. base+30: keep gf < g < n
             if (n - base < 31) v = 0x7fffffffu >> (31 - (n - base));
             if (gf + 1 - base >= 31) v = 0u;
