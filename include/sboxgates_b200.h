@@ -209,6 +209,13 @@ int sbg_finish7(sbg_handle *h, uint64_t key, const uint8_t *outer_order,
 int sbg_plan_tickets(int width, int prefix_gates, int n, uint32_t excluded, int mode,
                      uint64_t waves, uint64_t *out);
 
+/* Test hook, no device needed: the ticket tables of search_7lut phase 1's weighted form (4-gate
+   prefixes cut into groups of `group_pairs` (e,f) pairs, tickets numbered in lexicographic order of
+   (prefix, group); 7 <= n <= 72).  out[0] = tickets of the whole sweep, out[1 + 76 * (r-1) + x] =
+   tickets of all ways to choose r more prefix gates the first of which is >= x (r = 1..4). */
+#define SBG_WEIGHTED_ROW 76
+int sbg_weighted_tickets(int n, uint32_t group_pairs, uint32_t *out);
+
 /* Row k of the ordering tables (lut.c:189-229 for width 5, lut.c:396-415 for width 7). */
 int sbg_ordering_row(int width, int k, int *row);
 /* Closed form of get_lut_function without the random fill (lut.c:79-103): returns 1 and the

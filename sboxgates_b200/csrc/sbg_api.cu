@@ -187,6 +187,7 @@ struct sbg_handle {
   int opt_head_waves = 0;   // SBG_HEAD_WAVES: size of the chunked head in waves of warps (0 = default)
   int opt_pdl = 1;          // SBG_PDL: programmatic dependent launch between the kernels of a chain
   int opt_speculate = 1;    // SBG_SPECULATE: see enqueue_chain
+  int opt_group_chunks = 6; // SBG_GROUP_CHUNKS: chunks of 32 pairs per weighted phase-1 ticket (0 = whole prefixes)
   int opt_packed = 1;       // SBG_PACKED: phase 1 keeps two parts per register where <= 15 last gates remain
   int opt_decomp_filter = 1;  // SBG_DECOMP_FILTER: lane-parallel stage-1 filter of phase 2 (0 = ballot form only)
   int opt_batch_conc = 2;   // SBG_BATCH_CONC: phase-1 prefixes per ticket while several chains share
@@ -628,7 +629,33 @@ struct FilterPlan {
   bool five = false;
   uint64_t seg_base = 0;       // first ticket of this launch (sweeps larger than the ticket table)
   uint32_t list_base = 0;      // list entries earlier segments produced
+  WeightedTickets wt;          // group_pairs != 0: every ticket is a (prefix, group of pairs)
 };
+
+// Ticket tables of the weighted form (see WeightedTickets): f(d) tickets for a prefix whose last
+// gate is d, suffix sums level by level.
+void build_weighted(int n, uint32_t group_pairs, WeightedTickets *wt) {
+  memset(wt, 0, sizeof *wt);
+  const int np = n - 3;   // prefix elements are < np (three more gates follow)
+  if (np < 4 || np >= kWeightedRow || group_pairs == 0) return;
+  wt->group_pairs = group_pairs;
+  uint64_t prev[kWeightedRow + 1] = {0}, cur[kWeightedRow + 1];
+  // level 1: first (= only) element d >= x
+  for (int x = np - 1; x >= 0; x--) {
+    const uint64_t r = (uint64_t)(n - x - 2);
+    const uint64_t pairs = r >= 2 ? r * (r - 1) / 2 : 0;
+    const uint64_t f = std::max<uint64_t>(1, (pairs + group_pairs - 1) / group_pairs);
+    prev[x] = prev[x + 1] + f;
+  }
+  for (int x = 0; x < kWeightedRow; x++) wt->w[0][x] = (uint32_t)prev[x];
+  for (int r = 2; r <= 4; r++) {   // level r: first element a in [x, np - r], then r-1 more above it
+    memset(cur, 0, sizeof cur);
+    for (int x = np - r; x >= 0; x--) cur[x] = cur[x + 1] + prev[x + 1];
+    for (int x = 0; x < kWeightedRow; x++) wt->w[r - 1][x] = (uint32_t)cur[x];
+    memcpy(prev, cur, sizeof cur);
+  }
+  wt->total = wt->w[3][0];
+}
 
 template <int P>
 FilterPlan plan_filter_p(const sbg_handle *h, const sbg_lane &L, const sbg_handle::HostProblem &hp,
@@ -649,6 +676,17 @@ FilterPlan plan_filter_p(const sbg_handle *h, const sbg_lane &L, const sbg_handl
   fp.chunk_tickets = (fp.pl.items + kDeal * nparts - 1) / (kDeal * nparts) * kDeal;
   fp.batch = fp.pl.all ? 1 : pick_batch(h, fp.tickets, n, P == 4 ? 4 : 6);
   if (fp.max_warps > 0) fp.batch = 1;
+  fp.wt.group_pairs = 0;
+  // Weighted tickets: a chain that has the device to itself, 4-gate prefixes, no head, no retry
+  // (chains that share the device fill each other's tails and prefer fewer, larger tickets).
+  if (P == 4 && !retry && !h->concurrent && h->opt_group_chunks > 0 && h->opt_batch <= 0
+      && fp.pl.items == 0 && n >= 7 && n <= kWeightedMaxGates) {
+    build_weighted(n, 32u * (uint32_t)h->opt_group_chunks, &fp.wt);
+    if (fp.wt.group_pairs != 0) {
+      fp.tickets = ((uint64_t)fp.wt.total + nparts - 1) / nparts;
+      fp.batch = 1;
+    }
+  }
   fp.ticket_bound = fp.chunk_tickets + (fp.tickets + 2 * kDeal) / fp.batch + 2 + kTicketSlack;
   const uint64_t left = fp.ticket_bound > seg_base ? fp.ticket_bound - seg_base : kTicketSlack;
   fp.tickets_cap = std::min<uint64_t>(left, h->ticket_table_max + kTicketSlack);
@@ -687,7 +725,7 @@ int launch_filter7_pm_p(sbg_handle *h, sbg_lane &L, const FilterPlan &fp, int pa
         list_cap, (int)fp.batch, fp.max_warps,                                                 \
         pl.all ? (unsigned long long)fp.total : pl.t_offset, pl.items, std::max(1, pl.chunks), \
         (unsigned long long)fp.chunk_tickets, (unsigned long long)fp.seg_base,                 \
-        h->opt_packed ? 15 : 0);                                                               \
+        h->opt_packed ? 15 : 0, fp.wt);                                                        \
   }
   const bool shifted = P == 4 && (h->opt_shift >= 0 ? h->opt_shift != 0 && n <= 63
                                                      : n <= kShiftMaxGates);
@@ -1351,6 +1389,19 @@ int sbg_plan_tickets(int width, int prefix_gates, int n, uint32_t excluded, int 
   return SBG_OK;
 }
 
+int sbg_weighted_tickets(int n, uint32_t group_pairs, uint32_t *out) {
+  static_assert(SBG_WEIGHTED_ROW == kWeightedRow, "header and device code agree on the row length");
+  if (out == nullptr || n < 7 || n > kWeightedMaxGates || group_pairs == 0) return SBG_ERR_ARG;
+  WeightedTickets wt;
+  build_weighted(n, group_pairs, &wt);
+  if (wt.group_pairs == 0) return SBG_ERR_ARG;
+  out[0] = wt.total;
+  for (int r = 0; r < 4; r++) {
+    for (int x = 0; x < kWeightedRow; x++) out[1 + kWeightedRow * r + x] = wt.w[r][x];
+  }
+  return SBG_OK;
+}
+
 int sbg_ordering_row(int width, int k, int *row) {
   build_host_tables();
   if (row == nullptr) return SBG_ERR_ARG;
@@ -1433,6 +1484,9 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_BATCH") != nullptr) h->opt_batch = atoi(getenv("SBG_BATCH"));
   if (getenv("SBG_PM_PREFIX") != nullptr) h->opt_pm_prefix = atoi(getenv("SBG_PM_PREFIX"));
   if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
+  if (getenv("SBG_GROUP_CHUNKS") != nullptr) {
+    h->opt_group_chunks = std::max(0, std::min(64, atoi(getenv("SBG_GROUP_CHUNKS"))));
+  }
   if (getenv("SBG_PACKED") != nullptr) h->opt_packed = atoi(getenv("SBG_PACKED")) != 0;
   if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;
   if (getenv("SBG_HEAD_WAVES") != nullptr) h->opt_head_waves = atoi(getenv("SBG_HEAD_WAVES"));

@@ -745,6 +745,49 @@ __global__ void __launch_bounds__(kThreads) k_decomp5(const DevProblem *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weighted tickets (phase 1, 4-gate prefixes, n <= kWeightedMaxGates).  A whole prefix as one ticket
+// is too coarse where a warp's balanced share of the sweep is short: prefix (a,b,c,d) has
+// C(n-d-2, 2) pairs -- 19 chunks of 32 for the first prefixes at n = 40 -- and such prefixes recur
+// all through the lexicographic order (every (a,b,c) block starts with a small d).  So a prefix is
+// cut into groups of `group_pairs` pairs, f(d) = ceil(pairs / group_pairs) tickets, numbered in
+// lexicographic order of (prefix, group): ticket numbers stay monotone in the order of the list, which
+// is all the ordered emission and the stop rule need.  Ticket -> (prefix, group) is the same ballot
+// search as unrank_prefix_warp with f-weighted counts in place of binomials:
+//   w[r-1][x] = total tickets of the sequences of r more prefix elements whose first is >= x
+// (host-built suffix sums, travelling as a kernel argument).
+constexpr int kWeightedMaxGates = 72;
+constexpr int kWeightedRow = 76;
+struct WeightedTickets {
+  uint32_t group_pairs;   // 0 = not in use
+  uint32_t total;         // tickets of the whole sweep = w[3][0]
+  uint32_t w[4][kWeightedRow];
+};
+
+__device__ __forceinline__ void unrank_weighted_warp(uint32_t t, int np,
+    const uint32_t (*__restrict__ w)[kWeightedRow], int *pre, uint32_t &group, int lane) {
+  int x0 = 0;
+#pragma unroll
+  for (int pos = 0; pos < 4; pos++) {
+    const int r = 4 - pos;
+    const uint32_t *wr = w[r - 1];
+    const uint32_t total = wr[x0];
+    int cnt = 0;
+    for (int y0 = x0;; y0 += 32) {
+      const int y = y0 + lane;
+      const bool le = y <= np - r && total - wr[min(y, kWeightedRow - 1)] <= t;
+      const uint32_t bal = __ballot_sync(kFull, le);
+      cnt += __popc(bal);
+      if (bal != 0xffffffffu) break;
+    }
+    const int e = x0 + cnt - 1;
+    t -= total - wr[e];
+    pre[pos] = e;
+    x0 = e + 1;
+  }
+  group = t;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Phase 1 of search_7lut, position-major form (lut.c:294-327).
 //
 // One warp per 4-gate prefix (a,b,c,d); lanes take the (e,f) pairs; the last gate g is not
@@ -780,9 +823,10 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     unsigned long long tickets_cap, int part, int nparts, unsigned long long list_cap, int batch,
     int max_warps, unsigned long long t_offset, unsigned long long chunk_items,
     int chunks_per_prefix, unsigned long long chunk_tickets, unsigned long long seg_base,
-    int packed_gates) {
+    int packed_gates, const WeightedTickets wt) {
   constexpr int K = 7, NC = 1 << P, NP = P == 4 ? 4 : 2;
   extern __shared__ uint32_t smem[];
+  __shared__ uint32_t s_wt[4][kWeightedRow];
   // Work is handed out through one ordered ticket counter, in lexicographic order, under one stop
   // rule (no new ticket once the list cap is reached; what was handed out is finished).  Two kinds
   // of ticket:
@@ -831,6 +875,11 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
   for (int p = warp; p < m; p += kWarpsPerCta) {
     if (lane < (ngw >> 1)) {
       __pipeline_memcpy_async(s_xr + p * ngw + 2 * lane, &prob->xr[p][2 * lane], 8);
+    }
+  }
+  if (P == 4 && wt.group_pairs != 0) {
+    for (int i = threadIdx.x; i < 4 * kWeightedRow; i += blockDim.x) {
+      s_wt[i / kWeightedRow][i % kWeightedRow] = wt.w[i / kWeightedRow][i % kWeightedRow];
     }
   }
   stage_tables(s_tabs, prob, NW, npad);
@@ -916,12 +965,20 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     // one hands out tickets seg_base, seg_base + 1, ... and indexes its table from zero.
     // Dealt to the parts of a sharded search in blocks of kDeal consecutive items, see k_sweep.
     const unsigned long long bg = seg_base + b;
-    const bool chunked = bg < chunk_tickets;
-    const uint64_t lt = chunked ? bg : (bg - chunk_tickets) * (uint64_t)batch;
+    const bool weighted = P == 4 && wt.group_pairs != 0;   // every ticket = (prefix, group of pairs)
+    const bool chunked = !weighted && bg < chunk_tickets;
+    const uint64_t lt = (chunked || weighted) ? bg : (bg - chunk_tickets) * (uint64_t)batch;
     const uint64_t dealt = (lt / kDeal) * kDeal * (uint64_t)nparts + (uint64_t)part * kDeal
         + (lt % kDeal);
     bool valid = true;
-    if (chunked) {
+    if (weighted) {
+      if (dealt >= (uint64_t)wt.total) {   // past the end: every later ticket is, too
+        if (lane == 0) tcount[b] = 0;
+        break;
+      }
+      t_first = 0;
+      t_end = 1;
+    } else if (chunked) {
       valid = dealt < chunk_items;   // the last deal block is shorter for some parts
       t_first = dealt / (uint64_t)chunks_per_prefix;
       t_end = t_first + 1;
@@ -948,7 +1005,17 @@ __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(co
     if (valid) {
     int pre[P];
     uint64_t unused_rank;
-    unrank_prefix_warp<P, K, false>(t_first, chunked ? n_allowed : n, pre, unused_rank, lane);
+    if constexpr (P == 4) {
+      if (weighted) {
+        uint32_t group;
+        unrank_weighted_warp((uint32_t)dealt, n - (K - P), s_wt, pre, group, lane);
+        q_begin = group * wt.group_pairs;
+        q_limit = q_begin + wt.group_pairs;
+      }
+    }
+    if (!weighted) {
+      unrank_prefix_warp<P, K, false>(t_first, chunked ? n_allowed : n, pre, unused_rank, lane);
+    }
     if (chunked) {   // index among the allowed gates -> gate number (excluded gates are < 8)
 #pragma unroll
       for (int i = 0; i < P; i++) {

@@ -56,6 +56,7 @@ SIGNATURES = {
     "sbg_launch_count": (C.c_uint64, [C.c_void_p]),
     "sbg_plan_tickets": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint64,
                                    C.POINTER(C.c_uint64)]),
+    "sbg_weighted_tickets": (C.c_int, [C.c_int, C.c_uint32, C.POINTER(C.c_uint32)]),
     "sbg_last_kernel_ms": (C.c_float, [C.c_void_p, C.c_int]),
     "sbg_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "sbg_transfer_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

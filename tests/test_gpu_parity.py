@@ -217,8 +217,9 @@ def test_paths_agree(engine):
 def test_launch_modes_agree(engine):
     """The kernels of a chain are launched with programmatic dependent launch (each starts while its
     predecessor drains); with SBG_PDL=0 they are plainly stream-ordered, with SBG_TIMING=1 events sit
-    between them; SBG_PACKED=0 keeps phase 1 on one part per accumulator register throughout.  Hit
-    lists and search results must be identical in all modes."""
+    between them; SBG_PACKED=0 keeps phase 1 on one part per accumulator register throughout;
+    SBG_GROUP_CHUNKS sets how phase 1's prefixes are cut into tickets (0 = whole prefixes).  Hit lists
+    and search results must be identical in all modes."""
     import subprocess
     import sys
     code = (
@@ -235,11 +236,12 @@ def test_launch_modes_agree(engine):
         "import json; print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
     outs = {}
     for mode, env in (("pdl", {}), ("plain", {"SBG_PDL": "0"}), ("timed", {"SBG_TIMING": "1"}),
-                      ("unpacked", {"SBG_PACKED": "0"})):
+                      ("unpacked", {"SBG_PACKED": "0"}), ("whole-prefix", {"SBG_GROUP_CHUNKS": "0"}),
+                      ("groups-of-5", {"SBG_GROUP_CHUNKS": "5"})):
         res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env),
                              capture_output=True, text=True, check=True)
         outs[mode] = res.stdout.strip().splitlines()[-1]
-    assert outs["pdl"] == outs["plain"] == outs["timed"] == outs["unpacked"]
+    assert len(set(outs.values())) == 1, sorted(outs)
     import json
     assert sum(len(x) for x in json.loads(outs["pdl"])[0::3]) > 0
 

@@ -128,6 +128,42 @@ def test_ticket_plan_covers_the_allowed_prefixes_in_order():
     assert lib.sbg_plan_tickets(6, 4, 30, 0, 1, 1, out) != 0
 
 
+def test_weighted_ticket_tables_number_prefix_groups_in_order():
+    """sbg_weighted_tickets (host planning code, no device needed): phase 1's weighted tickets cut a
+    4-gate prefix (a,b,c,d) into ceil(C(n-d-2, 2) / group_pairs) groups and number (prefix, group) in
+    lexicographic order.  The tables must unrank every ticket -- by the search the kernel does: per
+    element, the largest y whose 'tickets before' count is <= t -- to exactly that enumeration."""
+    import ctypes as C
+    import itertools
+    from math import comb
+    lib = native.load_library()
+    row = 76
+    out = (C.c_uint32 * (1 + 4 * row))()
+    for n, gp in ((7, 32), (9, 64), (16, 32), (22, 64), (30, 128), (40, 64)):
+        assert lib.sbg_weighted_tickets(n, gp, out) == 0
+        total = int(out[0])
+        w = [[int(out[1 + row * r + x]) for x in range(row)] for r in range(4)]
+        np_ = n - 3
+        want = []
+        for pre in itertools.combinations(range(np_), 4):
+            pairs = comb(n - pre[3] - 2, 2)
+            for g in range(max(1, -(-pairs // gp))):
+                want.append((pre, g))
+        assert total == len(want) == w[3][0]
+        step = max(1, total // 4000)
+        for t0 in list(range(0, total, step)) + [total - 1]:
+            t, x0, pre = t0, 0, []
+            for pos in range(4):
+                r = 4 - pos
+                wr = w[r - 1]
+                e = max(y for y in range(x0, np_ - r + 1) if wr[x0] - wr[y] <= t)
+                t -= wr[x0] - wr[e]
+                pre.append(e)
+                x0 = e + 1
+            assert (tuple(pre), t) == want[t0], (n, gp, t0)
+    assert lib.sbg_weighted_tickets(73, 32, out) != 0 and lib.sbg_weighted_tickets(20, 0, out) != 0
+
+
 def test_graph_loader_and_verifier(tmp_path):
     """sboxgates_b200/graph.py: gates.xsd loader (the checks of state.c:260-411) + functional check."""
     from sboxgates_b200 import graph as G
