@@ -188,6 +188,7 @@ struct sbg_handle {
   int opt_pdl = 1;          // SBG_PDL: programmatic dependent launch between the kernels of a chain
   int opt_speculate = 1;    // SBG_SPECULATE: see enqueue_chain
   int opt_group_chunks = 6; // SBG_GROUP_CHUNKS: chunks of 32 pairs per weighted phase-1 ticket (0 = whole prefixes)
+  int opt_group_chunks_conc = 0;  // SBG_GROUP_CHUNKS_CONC: the same while several chains share the device
   int opt_packed = 1;       // SBG_PACKED: phase 1 keeps two parts per register where <= 15 last gates remain
   int opt_decomp_filter = 1;  // SBG_DECOMP_FILTER: lane-parallel stage-1 filter of phase 2 (0 = ballot form only)
   int opt_batch_conc = 2;   // SBG_BATCH_CONC: phase-1 prefixes per ticket while several chains share
@@ -679,9 +680,10 @@ FilterPlan plan_filter_p(const sbg_handle *h, const sbg_lane &L, const sbg_handl
   fp.wt.group_pairs = 0;
   // Weighted tickets: a chain that has the device to itself, 4-gate prefixes, no head, no retry
   // (chains that share the device fill each other's tails and prefer fewer, larger tickets).
-  if (P == 4 && !retry && !h->concurrent && h->opt_group_chunks > 0 && h->opt_batch <= 0
+  const int group_chunks = h->concurrent ? h->opt_group_chunks_conc : h->opt_group_chunks;
+  if (P == 4 && !retry && group_chunks > 0 && h->opt_batch <= 0
       && fp.pl.items == 0 && n >= 7 && n <= kWeightedMaxGates) {
-    build_weighted(n, 32u * (uint32_t)h->opt_group_chunks, &fp.wt);
+    build_weighted(n, 32u * (uint32_t)group_chunks, &fp.wt);
     if (fp.wt.group_pairs != 0) {
       fp.tickets = ((uint64_t)fp.wt.total + nparts - 1) / nparts;
       fp.batch = 1;
@@ -1486,6 +1488,9 @@ int sbg_create(sbg_handle **out, int device) {
   if (getenv("SBG_HEAD") != nullptr) h->opt_head = std::max(0, std::min(2, atoi(getenv("SBG_HEAD"))));
   if (getenv("SBG_GROUP_CHUNKS") != nullptr) {
     h->opt_group_chunks = std::max(0, std::min(64, atoi(getenv("SBG_GROUP_CHUNKS"))));
+  }
+  if (getenv("SBG_GROUP_CHUNKS_CONC") != nullptr) {
+    h->opt_group_chunks_conc = std::max(0, std::min(64, atoi(getenv("SBG_GROUP_CHUNKS_CONC"))));
   }
   if (getenv("SBG_PACKED") != nullptr) h->opt_packed = atoi(getenv("SBG_PACKED")) != 0;
   if (getenv("SBG_SHIFT") != nullptr) h->opt_shift = atoi(getenv("SBG_SHIFT")) != 0;

@@ -33,7 +33,8 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rs = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 engines = {"pm4": engine(SBG_PM_PREFIX=4), "pm5": engine(SBG_PM_PREFIX=5),
            "plain": engine(SBG_PDL=0), "pm4_b1": engine(SBG_PM_PREFIX=4, SBG_BATCH=1),
-           "pm5_b16": engine(SBG_PM_PREFIX=5, SBG_BATCH=16)}
+           "pm5_b16": engine(SBG_PM_PREFIX=5, SBG_BATCH=16),
+           "pm4_g1": engine(SBG_PM_PREFIX=4, SBG_GROUP_CHUNKS=1, SBG_PACKED=0)}
 e5 = {"fused": engine(SBG_SEARCH5="fused"), "two": engine(SBG_SEARCH5="two")}
 e7_plain = engine(SBG_DECOMP_FILTER=0)   # phase 2 without the lane-parallel stage-1 filter
 sbox = S.rijndael_sbox()
