@@ -1806,23 +1806,25 @@ __global__ void __launch_bounds__(1024) k_begin(DevProblem *__restrict__ prob,
 // ------------------------------------------------------------------------------------------------
 // Phase 2 of search_7lut (lut.c:416-484): one warp per feasible 7-tuple.
 
-__device__ __forceinline__ uint32_t compress16(uint32_t r16, int b, int z) {
-  // Keeps the 8 bits of a 16-bit set over v4 whose index has bit b equal to z, in order.
+__device__ __forceinline__ uint32_t compress16x2(uint32_t r, int b, int z) {
+  // r holds two 16-bit sets over v4 (low and high half).  Of each, keeps the 8 bits whose index has
+  // bit b equal to z, in order: results in bits 0..7 and 16..23.
   uint32_t t;
   switch (b) {
     case 3:
-      return (r16 >> (8 * z)) & 0xffu;
+      return (r >> (8 * z)) & 0x00ff00ffu;
     case 2:
-      t = r16 >> (4 * z);
-      return (t & 0x0fu) | ((t >> 4) & 0xf0u);
+      t = r >> (4 * z);
+      return (t & 0x000f000fu) | ((t >> 4) & 0x00f000f0u);
     case 1:
-      t = r16 >> (2 * z);
-      return (t & 0x03u) | ((t >> 2) & 0x0cu) | ((t >> 4) & 0x30u) | ((t >> 6) & 0xc0u);
+      t = r >> (2 * z);
+      return (t & 0x00030003u) | ((t >> 2) & 0x000c000cu) | ((t >> 4) & 0x00300030u)
+          | ((t >> 6) & 0x00c000c0u);
     default:
-      t = (r16 >> z) & 0x5555u;
-      t = (t | (t >> 1)) & 0x3333u;
-      t = (t | (t >> 2)) & 0x0f0fu;
-      return (t | (t >> 4)) & 0xffu;
+      t = (r >> z) & 0x55555555u;
+      t = (t | (t >> 1)) & 0x33333333u;
+      t = (t | (t >> 2)) & 0x0f0f0f0fu;
+      return (t | (t >> 4)) & 0x00ff00ffu;
   }
 }
 
@@ -1988,6 +1990,7 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
   __shared__ uint8_t s_fo[kWarpsPerCta][256];
   __shared__ uint32_t s_src7[25 * 32];   // copy of DevTables::src7
   __shared__ uint32_t s_H[kWarpsPerCta][24];
+  __shared__ uint32_t s_row_best[kWarpsPerCta][4];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -2134,26 +2137,31 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
 
       const int k0 = c_j_first_k[j];
       const int nrows = c_j_rows[j];
-      for (int row = 0; row < nrows && !found; row++) {
-        const int k = k0 + row;
-        const int b = c_row_b[k];
-        uint32_t best_local = 0xffffffffu;
-        for (int i0 = 0; i0 < ns; i0 += 32) {
-          const bool have = i0 + lane < ns;
-          const int fo = have ? fo_list[i0 + lane] : 0;
-          uint32_t r1 = 0, r0 = 0;
+      // per row of this outer triple: minimum (outer position, middle position) over the survivors;
+      // the survivors' merged sets r1 / r0 do not depend on the row, so the rows are the inner loop
+      uint32_t *row_best = s_row_best[warp];   // (shared memory: registers are short here)
+      __syncwarp();
+      if (lane < 4) row_best[lane] = 0xffffffffu;
+      __syncwarp();
+      for (int i0 = 0; i0 < ns; i0 += 32) {
+        const bool have = i0 + lane < ns;
+        const int fo = have ? fo_list[i0 + lane] : 0;
+        uint32_t r1 = 0, r0 = 0;
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            if ((fo >> u) & 1) r1 |= W[u]; else r0 |= W[u];
-          }
-          // The four inner cells (x, g): A = middle patterns with a masked 1, B = with a masked 0.
+        for (int u = 0; u < 8; u++) {
+          if ((fo >> u) & 1) r1 |= W[u]; else r0 |= W[u];
+        }
+#pragma unroll 1
+        for (int row = 0; row < nrows; row++) {
+          const int b = c_row_b[k0 + row];
+          // The four inner cells (x, g): A = middle patterns with a masked 1, B = with a masked 0
+          // (both compressed at once: they are the two halves of r1 / r0).
           // If both are non-empty, fm must send A to one value and B to the other: fm & S in {A, B}.
           uint32_t cs[4], ca[4], cb[4];
 #pragma unroll
           for (int ci = 0; ci < 4; ci++) {
-            const uint32_t R = (ci & 2) ? r1 : r0;
-            const uint32_t A = compress16(R & 0xffffu, b, ci & 1);
-            const uint32_t B = compress16(R >> 16, b, ci & 1);
+            const uint32_t AB = compress16x2((ci & 2) ? r1 : r0, b, ci & 1);
+            const uint32_t A = AB & 0xffu, B = AB >> 16;
             const bool act = A != 0 && B != 0;
             cs[ci] = act ? (A | B) : 0u;   // inactive: empty support, both choices identical
             ca[ci] = act ? A : 0u;
@@ -2193,12 +2201,19 @@ __global__ void __launch_bounds__(kThreads) k_decomp7(const DevProblem *__restri
           }
           uint32_t cand = 0xffffffffu;
           if (have && best_pm < 256) cand = ((uint32_t)s_pos[fo] << 8) | best_pm;
-          best_local = min(best_local, __reduce_min_sync(kFull, cand));
+          cand = __reduce_min_sync(kFull, cand);
+          if (lane == 0 && cand < row_best[row]) row_best[row] = cand;
         }
-        if (best_local != 0xffffffffu) {
-          key = (idx << 23) | ((uint64_t)k << 16) | best_local;
-          found = true;
-        }
+      }
+      __syncwarp();
+      // the first row (= the smallest ordering number) with a match decides
+      const uint32_t mine = lane < nrows ? row_best[lane] : 0xffffffffu;
+      const uint32_t hit_rows = __ballot_sync(kFull, mine != 0xffffffffu);
+      if (hit_rows != 0) {
+        const int row_hit = __ffs(hit_rows) - 1;
+        key = (idx << 23) | ((uint64_t)(k0 + row_hit) << 16)
+            | (uint64_t)__shfl_sync(kFull, mine, row_hit);
+        found = true;
       }
     }
     if (found) {
