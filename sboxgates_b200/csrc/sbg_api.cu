@@ -975,7 +975,9 @@ int prep_ctas(const sbg_handle::HostProblem &hp, const BeginArgs &a) {
 
 int scan_ctas(const sbg_handle *h, int n) {
   const int pairs = n * (n - 1) / 2;
-  return std::max(1, std::min(4 * h->sm_count, (pairs + 63) / 64));
+  // one position pair per warp (32 warps per block) while the device has room: the scan's result is
+  // the first thing a node's host code waits for
+  return std::max(1, std::min(4 * h->sm_count, (pairs + 31) / 32));
 }
 
 int stage_problem(sbg_handle *h, int slot, const uint64_t *tables, int n, const uint64_t *target,
