@@ -218,8 +218,9 @@ def test_launch_modes_agree(engine):
     """The kernels of a chain are launched with programmatic dependent launch (each starts while its
     predecessor drains); with SBG_PDL=0 they are plainly stream-ordered, with SBG_TIMING=1 events sit
     between them; SBG_PACKED=0 keeps phase 1 on one part per accumulator register throughout;
-    SBG_GROUP_CHUNKS sets how phase 1's prefixes are cut into tickets (0 = whole prefixes).  Hit lists
-    and search results must be identical in all modes."""
+    SBG_GROUP_CHUNKS sets how phase 1's prefixes are cut into tickets (0 = whole prefixes).  Hit lists,
+    search results and -- for sweeps that run to the end -- the T-unit counts must be identical in all
+    modes."""
     import subprocess
     import sys
     code = (
@@ -232,7 +233,7 @@ def test_launch_modes_agree(engine):
         "    out.append(eng.filter7_part(0, 1).tolist())\n"
         "    seed = np.random.RandomState(n).bytes(128)\n"
         "    for fn in (sb.search_5lut, sb.search_7lut):\n"
-        "        r = fn(eng, tabs, tgt, mask, inb, sb.Xorshift1024(seed)); out.append([int(r.found)] + [int(x) for x in r.ret])\n"
+        "        r = fn(eng, tabs, tgt, mask, inb, sb.Xorshift1024(seed)); out.append([int(r.found), -1 if (r.found or r.tuples_feasible >= 100000) else int(r.tuples_swept)] + [int(x) for x in r.ret])\n"
         "import json; print(json.dumps(out))\n" % (S.ROOT, os.path.join(S.ROOT, "tests")))
     outs = {}
     for mode, env in (("pdl", {}), ("plain", {"SBG_PDL": "0"}), ("timed", {"SBG_TIMING": "1"}),
