@@ -813,8 +813,12 @@ __device__ __forceinline__ void unrank_weighted_warp(uint32_t t, int np,
 // of the rows shifted down to the first possible g (31 gates per word, the target bit on top) in
 // its own shared-memory scratch; one word per position then covers every candidate of nearly every
 // prefix and the position loop does half the accumulates.
+// CTAs per SM the register allocation aims at: 3 for the shifted-window form (79 registers, nothing
+// spilled; measured at the end of round 2, after the overhead work: 1.204 -> 1.173 ms per bench step
+// against 2 CTAs with 113 registers -- in the middle of the round the same cap did not pay), 2 for the
+// two-word forms of larger n (a cap of 80 spills there).
 #ifndef SBG_FILTER_MIN_CTAS
-#define SBG_FILTER_MIN_CTAS 2
+#define SBG_FILTER_MIN_CTAS (SH ? 3 : 2)
 #endif
 template <int NW, int W, int P, bool FS, bool SH = false>
 __global__ void __launch_bounds__(kThreads, SBG_FILTER_MIN_CTAS) k_filter7_pm(const DevProblem *__restrict__ prob,
