@@ -809,10 +809,11 @@ __device__ __forceinline__ void unrank_weighted_warp(uint32_t t, int np,
 // the AND / OR accumulators then also tell which targets a part has seen (OR = some 1, AND = only 1s)
 // and the separate bookkeeping disappears from the inner loop.
 // SH ("shifted window", n <= 63, W = 1, FS): at small n a lane has few candidate last gates -- all of
-// them above the prefix -- so instead of aligned 64-gate windows the warp builds, per prefix, a copy
-// of the rows shifted down to the first possible g (31 gates per word, the target bit on top) in
-// its own shared-memory scratch; one word per position then covers every candidate of nearly every
-// prefix and the position loop does half the accumulates.
+// them above the prefix -- so instead of aligned 64-gate windows the CTA keeps, for every possible
+// first g (= window base 6 .. n-1), a copy of the rows shifted down to it (31 gates per word, the
+// target bit on top; (n - 6) * m words of shared memory, built once at the start of the kernel); one
+// word per position then covers every candidate of nearly every prefix and the position loop does
+// half the accumulates.  Windows with <= 15 gates use the PACKED form (see the cell loop).
 // CTAs per SM the register allocation aims at: 3 for the shifted-window form (79 registers, nothing
 // spilled; measured at the end of round 2, after the overhead work: 1.204 -> 1.173 ms per bench step
 // against 2 CTAs with 113 registers -- in the middle of the round the same cap did not pay), 2 for the
