@@ -364,6 +364,11 @@ def replay_record(eng, sb):
                      "units_per_s": (t_units + c_units) / secs, "t_units": t_units,
                      "c_units": c_units, "reference_seconds_when_recorded": ref_secs,
                      "parity": True}
+    if out:
+        out["note"] = ("through the Python mirror of the two-function interface (lut.py): each call "
+                       "includes 256 / 512 draws of the Python xorshift1024 and the ctypes marshalling "
+                       "of the state, which dominate the time per call; the `graph` record times the "
+                       "same path from C")
     return out
 
 
