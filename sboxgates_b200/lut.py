@@ -180,6 +180,23 @@ class LutEngine:
                                                ib.ctypes.data_as(native.i8p)))
         self._slot_n[slot] = tables.shape[0]
 
+    def prepare_state(self, tables, target, mask, inbits):
+        """Marshals a state's host buffers once (numpy -> pointers) for stage_prepared: a caller that
+        stages the same host arrays repeatedly, or wants the marshalling out of a timed region."""
+        tables, tp = _u64(tables)
+        target, gp = _u64(target)
+        mask, mp = _u64(mask)
+        ib = np.full(8, -1, dtype=np.int8)
+        ib[:len(inbits)] = inbits
+        return (tables, tp, target, gp, mask, mp, ib, ib.ctypes.data_as(native.i8p),
+                int(tables.shape[0]))
+
+    def stage_prepared(self, slot, prep):
+        """stage() on the result of prepare_state (which keeps the host buffers alive)."""
+        self._check(self.lib.sbg_stage_problem(self._h, slot, prep[1], prep[8], prep[3], prep[5],
+                                               prep[7]))
+        self._slot_n[slot] = prep[8]
+
     def use(self, slot):
         self._check(self.lib.sbg_use_problem(self._h, slot))
         self.n = self._slot_n[slot]
@@ -242,6 +259,24 @@ class LutEngine:
             keep.append(k)
         res = (SbgNodeResult * len(jobs))()
         self._check(self.lib.sbg_search_batch(self._h, len(jobs), arr, res))
+        return list(res)
+
+    def prepare_jobs(self, jobs):
+        """The job array of search_batch, built once: (array, keep-alive buffers, count)."""
+        arr = (SbgJob * len(jobs))()
+        keep = []
+        for i, j in enumerate(jobs):
+            job, k = self._job(j.get("slot", 0), j.get("order5"), j.get("outer"), j.get("middle"),
+                               j.get("gate_order"))
+            arr[i] = job
+            keep.append(k)
+        return arr, keep, len(jobs)
+
+    def search_batch_prepared(self, prepared):
+        """search_batch on the result of prepare_jobs."""
+        arr, _, count = prepared
+        res = (SbgNodeResult * count)()
+        self._check(self.lib.sbg_search_batch(self._h, count, arr, res))
         return list(res)
 
     def list7_device(self):
